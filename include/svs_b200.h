@@ -1,0 +1,188 @@
+/*
+ * svs_b200.h — C ABI of libsvs_b200.so, the B200 (sm_100a) implementation of the SVS-UNet
+ * separation hot path:  magnitude STFT -> UNet soft mask -> mask x mixture -> iSTFT overlap-add,
+ * plus the L1 training step through the same kernels.
+ *
+ * The reference (zouyuoz/SVS-UNet-PyTorch) has no FFI of its own: its hot path is reached through
+ * librosa (data.py) and torch.nn (model.py).  Each entry point below names the reference call
+ * site(s) it replaces.  The binding a maintainer adds on the reference side is a ctypes stub —
+ * see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every call returns 0 on success, a negative svs_status otherwise; the message is available
+ *     from svs_last_error() (thread local).  No C++ exception crosses this boundary.
+ *   - all data pointers are DEVICE pointers owned by the caller; the library never allocates or
+ *     frees caller-visible memory (a plan owns only its private repacked weights).
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*); calls are asynchronous,
+ *     never synchronise the device and are CUDA-graph capturable.
+ *   - there is no CPU path and no fallback: a device that is not compute capability 10.x, or a
+ *     geometry other than n_fft 1024 / hop 768 / 512x128 patches, is an error.
+ */
+#ifndef SVS_B200_H
+#define SVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVS_ABI_VERSION 1
+
+/* geometry of the path (reference config.py:47-51) */
+#define SVS_N_FFT        1024
+#define SVS_HOP          768
+#define SVS_N_BINS       513      /* rows of a *_spec.npy */
+#define SVS_PATCH_BINS   512      /* DC row dropped, reference inference.py:68 */
+#define SVS_PATCH_FRAMES 128      /* INPUT_LEN */
+
+typedef enum svs_status {
+  SVS_OK = 0,
+  SVS_ERR_INVALID_ARG = -1,
+  SVS_ERR_CUDA = -2,
+  SVS_ERR_UNSUPPORTED_ARCH = -3,
+  SVS_ERR_WORKSPACE = -4,
+  SVS_ERR_NOT_IMPLEMENTED = -5
+} svs_status;
+
+typedef enum svs_precision {
+  SVS_PRECISION_FP32 = 0,   /* fp32 activations + fp32 FMA (exact-arithmetic mode)            */
+  SVS_PRECISION_BF16 = 1,   /* bf16 NHWC activations, tcgen05 kind::f16 MMA, fp32 accumulate   */
+  SVS_PRECISION_TF32 = 2    /* fp32 NHWC activations, tcgen05 kind::tf32 MMA, fp32 accumulate  */
+} svs_precision;
+
+enum {
+  SVS_FLAG_APPLY_MASK = 1,  /* out = mix * mask (reference inference.py:107) instead of the mask   */
+  SVS_FLAG_INVERT     = 2   /* mask <- 1 - mask  (reference inference.py:102, --vocal_solo 0)       */
+};
+
+/* ------------------------------------------------------------------ lifecycle / diagnostics */
+int svs_version(void);                       /* == SVS_ABI_VERSION                              */
+const char* svs_last_error(void);            /* thread-local message of the last failing call   */
+int svs_device_check(int device);            /* SVS_OK iff `device` is compute capability 10.x  */
+
+/* ------------------------------------------------------------------ spectral front end (S1-S3)
+ * Replaces librosa.stft + librosa.magphase at reference data.py:79-81 and data.py:100-102
+ * (n_fft 1024, hop 768, periodic Hann, center=True, pad_mode="constant"), batched over a ragged
+ * set of songs.
+ *   audio        concatenated mono float32 songs; song s = audio[sample_off[s] .. sample_off[s+1])
+ *   sample_off   device int64 [n_songs+1]
+ *   frame_off    device int64 [n_songs+1]; frame_off[s+1]-frame_off[s] must equal 1 + len_s/768
+ *   max_frames   host: largest per-song frame count (grid sizing)
+ *   mag          float32 [total_frames][513]  == the Fortran-ordered (513,T) array librosa returns
+ *   phase        complex64 as float pairs [total_frames][513][2], unit phasors, 1+0j where mag==0;
+ *                may be NULL
+ *   song_max     float32 [n_songs] max magnitude per song (reference data.py:84); may be NULL
+ */
+int svs_stft_mag_phase(const float* audio, const int64_t* sample_off, const int64_t* frame_off,
+                       int n_songs, int64_t max_frames, float* mag, float* phase, float* song_max,
+                       void* stream);
+
+/* librosa.stft alone (reference data.py:79,100): raw complex64 spectrum [total_frames][513][2]. */
+int svs_stft_complex(const float* audio, const int64_t* sample_off, const int64_t* frame_off,
+                     int n_songs, int64_t max_frames, float* spec, void* stream);
+
+/* librosa.magphase alone (reference data.py:80,101) on n complex64 values. */
+int svs_magphase(const float* spec, int64_t n, float* mag, float* phase, void* stream);
+
+/* spec /= norm per song, norm==0 -> 1 (reference data.py:85,105).  `norm` is a device float32
+ * [n_songs] array (for the vocal stem it is the MIXTURE's song_max). */
+int svs_spec_normalize(float* mag, const int64_t* frame_off, const float* norm, int n_songs,
+                       int64_t total_frames, void* stream);
+
+/* ------------------------------------------------------------------ spectral back end (W1-W3)
+ * Replaces `librosa.istft(mag * phase, win_length=1024, hop_length=768)` at reference data.py:159:
+ * complex recombine, inverse real FFT, Hann window, deterministic gather-form overlap-add (no
+ * atomics), division by the window-sum-of-squares envelope, trim n_fft/2 on both ends.
+ *   wave         float32; song s occupies wave[wave_off[s] .. wave_off[s] + 768*(T_s-1))
+ *   song_peak    float32 [n_songs] max |y| per song (reference data.py:162); may be NULL
+ */
+int svs_istft_ola(const float* mag, const float* phase, const int64_t* frame_off,
+                  const int64_t* wave_off, int n_songs, int64_t max_frames, float* wave,
+                  float* song_peak, void* stream);
+
+/* y <- y / peak * target where peak > 0 (reference data.py:163-164, target 0.9). */
+int svs_wave_peak_normalize(float* wave, const int64_t* wave_off, const float* song_peak,
+                            int n_songs, int64_t total_samples, float target, void* stream);
+
+/* ------------------------------------------------------------------ UNet mask (U1-D6, I2-I4)
+ * Replaces UNet.forward (reference model.py:169-201) in eval mode followed by the mask
+ * application of reference inference.py:102,107.
+ */
+typedef struct svs_conv_params {      /* one conv / deconv block, tensors in torch layout, fp32 */
+  const float* weight;                /* Conv2d (Cout,Cin,5,5) / ConvTranspose2d (Cin,Cout,5,5) */
+  const float* bias;                  /* (Cout)                                                  */
+  const float* bn_weight;             /* (Cout) or NULL when the block has no BatchNorm (deconv6)*/
+  const float* bn_bias;
+  const float* bn_mean;               /* running_mean */
+  const float* bn_var;                /* running_var  */
+} svs_conv_params;
+
+typedef struct svs_unet_plan svs_unet_plan;   /* opaque; immutable after creation */
+
+/* layers[0..5] = conv1..conv6, layers[6..11] = deconv1..deconv6 (state_dict of model.py:47-109).
+ * Folds eval-mode BatchNorm (eps 1e-5) into weights/bias and repacks them for the kernels. The
+ * source tensors may be freed once the call's stream work has completed. */
+int svs_unet_plan_create(const svs_conv_params layers[12], int precision, void* stream,
+                         svs_unet_plan** plan_out);
+int svs_unet_plan_destroy(svs_unet_plan* plan);
+int svs_unet_plan_precision(const svs_unet_plan* plan);
+
+size_t svs_unet_workspace_bytes(const svs_unet_plan* plan, int batch);
+
+/* One batch of `batch` patches, each 512 bins x 128 frames.
+ *   in / out      float32; element (patch b, bin f, frame t) lives at
+ *                 base + patch_off[b] + f*stride_f + t*stride_t   (patch_off == NULL: b*stride_b)
+ *   in_frames     device int32 [batch] number of valid frames per patch (the rest are read as zero
+ *                 and not written: the zero padding / crop of reference inference.py:90-92,113-114);
+ *                 NULL = all 128
+ *   flags         SVS_FLAG_APPLY_MASK | SVS_FLAG_INVERT
+ *   workspace     device scratch of at least svs_unet_workspace_bytes(plan, batch), 1024-B aligned
+ */
+typedef struct svs_patch_view {
+  float* base;
+  const int64_t* patch_off;   /* device [batch] element offsets, or NULL */
+  int64_t stride_b;           /* used when patch_off == NULL */
+  int64_t stride_f;
+  int64_t stride_t;
+} svs_patch_view;
+
+int svs_unet_forward(const svs_unet_plan* plan, const svs_patch_view* in, const svs_patch_view* out,
+                     const int32_t* in_frames, int batch, int flags, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Debug / parity hook: copy an intermediate activation of the LAST svs_unet_forward call on this
+ * workspace out as fp32 NCHW.  layer 0..5 = conv1..conv6 outputs, 6..10 = deconv1..deconv5 outputs. */
+int svs_unet_read_activation(const svs_unet_plan* plan, int layer, int batch, const void* workspace,
+                             float* out_nchw, void* stream);
+
+/* Number of kernel launches svs_unet_forward enqueues for this plan/batch (bench bookkeeping). */
+int svs_unet_launch_count(const svs_unet_plan* plan, int batch);
+
+/* ------------------------------------------------------------------ training step (T1)
+ * Forward in train mode (batch-statistic BatchNorm with running-stat update, Dropout2d via explicit
+ * keep masks), masked-L1 loss of reference train.py:274-283 with crit = L1, and the backward pass.
+ * Parameters and gradients are the raw fp32 torch tensors of the state_dict (no plan).
+ */
+typedef struct svs_train_layer {
+  float* weight;  float* bias;                 /* parameters (read)                                 */
+  float* bn_weight; float* bn_bias;            /* NULL for deconv6                                   */
+  float* bn_running_mean; float* bn_running_var;   /* updated in place (momentum 0.1, unbiased var) */
+  float* grad_weight; float* grad_bias;        /* written (overwritten, not accumulated)            */
+  float* grad_bn_weight; float* grad_bn_bias;
+  const uint8_t* dropout_keep;                 /* device [batch][Cout] 0/1 or NULL (= keep all)     */
+} svs_train_layer;
+
+size_t svs_unet_train_workspace_bytes(int batch);
+
+/* loss_out: device float32 [3] = {total, vocal term, accompaniment term}; two_term: 1 = train.py
+ * form, 0 = vocal term only.  update_running_stats: 1 in training. */
+int svs_unet_train_step(const svs_train_layer layers[12], const float* mix, const float* voc,
+                        int batch, int two_term, int update_running_stats, float* loss_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVS_B200_H */

@@ -1,0 +1,675 @@
+// K3/K4: 5x5 stride-2 convolution and transposed convolution as implicit GEMM on the sm_100a
+// tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// GEMM view (reference model.py:52-108):   D[M = pixels][N = Cout] = A[M][K] * B[N][K]^T
+//   conv   : M runs over OUTPUT pixels, K = 25 taps x Cin.  The NHWC input [B][H][W][Ct] is viewed
+//            through a rank-5 tensor map  (pw*Ct + c, W/2, ph, H/2, B)  — rows and columns split
+//            by parity — so that tap (kh, kw) of a stride-2 window is a plain box at offset
+//            (dw, ph, dh) = (floor((kw-2)/2), (kh-2) mod 2, floor((kh-2)/2)); zero padding is the TMA
+//            out-of-bounds fill.
+//   deconv : 4 sub-pixel phases (py, px); each is a stride-1 conv over the INPUT grid with 3x3 /
+//            3x2 / 2x3 / 2x2 taps (oh = 2 ih - 2 + kh  =>  kh = py (mod 2), ih = m + (py + 2 - kh)/2),
+//            its output interleaved at (2m + py, 2n + px).
+//   A tile = 128 pixels (bw x bh x nb box) x one swizzle row of K (128/64/32 bytes), landed by one
+//            TMA into the canonical K-major swizzled layout the UMMA descriptor expects.
+//   B tile = BLOCK_N x the same K slice of the BatchNorm-folded, pre-packed weights.
+//   Epilogue: TMEM -> registers (tcgen05.ld) -> bias + LeakyReLU/ReLU -> bf16/fp32 -> stored at
+//            the channel offset of the consumer's concat buffer (torch.cat as an addressing mode).
+//   Split-K (deep layers, few pixels, many taps): partial fp32 tiles + a deterministic reduction.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include "unet_internal.cuh"
+
+#include <cudaTypedefs.h>
+#include <cstdlib>
+#include <mutex>
+
+namespace svs {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA
+template <bool kTf32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if constexpr (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrives on the mbarrier once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand descriptor for a [rows][kSwz bytes] tile in the kSwz-byte swizzled canonical layout
+// (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61.
+template <int kSwz>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = kSwz == 128 ? 2 : (kSwz == 64 ? 4 : 6);
+  constexpr uint64_t sbo = (8 * kSwz) >> 4;      // 8-row core-matrix group pitch
+  return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
+         (layout << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 @4, a/b format @7/@10, K-major both, N>>3 @17, M>>4 @24
+template <bool kTf32, int kN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  const uint32_t fmt = kTf32 ? 2u : 1u;          // TF32 : BF16
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kN >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+  const TcChunk* chunks;
+  int n_chunks[4], chunk_begin[4], py[4], px[4];
+  int n_phases, split_k;
+  int ntw, nth;                  // M tiles along w and h of the pixel grid
+  int bw, bh, nb;
+  int batch;
+  int block_k;                   // K elements per chunk
+  void* out;
+  int out_pitch, out_coff, hout, wout, out_scale;
+  const float* bias;
+  int act;
+  float* partial;
+  int m_pad;                     // rows per (phase, split) slab of `partial`
+  int cout;
+};
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+  if (act == ACT_LEAKY) return v > 0.0f ? v : 0.2f * v;
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* dst, const float (&f)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void store16(float* dst, const float (&f)[16]) {
+  float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+
+constexpr int kTcThreads = 192;
+
+template <int kBlockN, int kSwz, int kStages>
+constexpr size_t tc_smem_bytes() {
+  return static_cast<size_t>(kStages) * (128 + kBlockN) * kSwz + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
+
+template <typename OutT, bool kTf32, int kBlockN, int kSwz, int kStages>
+__global__ void __launch_bounds__(kTcThreads)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b0,
+               const __grid_constant__ CUtensorMap tmap_b1, const __grid_constant__ CUtensorMap tmap_b2,
+               const __grid_constant__ CUtensorMap tmap_b3, const TcParams p) {
+  constexpr int kABytes = 128 * kSwz;
+  constexpr int kBBytes = kBlockN * kSwz;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = kBlockN < 32 ? 32 : kBlockN;
+  constexpr int kMmaPerChunk = kSwz / 32;          // UMMA_K is 32 bytes for bf16 (16) and tf32 (8)
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int phase = blockIdx.z / p.split_k;
+  const int split = blockIdx.z - phase * p.split_k;
+  const int n_chunks = p.n_chunks[phase];
+  const int per_split = (n_chunks + p.split_k - 1) / p.split_k;
+  const int c_begin = split * per_split;
+  const int c_end = min(n_chunks, c_begin + per_split);
+  const int n_iter = max(0, c_end - c_begin);
+
+  const int tw = blockIdx.x % p.ntw;
+  const int th = (blockIdx.x / p.ntw) % p.nth;
+  const int tb = blockIdx.x / (p.ntw * p.nth);
+  const int n0 = blockIdx.y * kBlockN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(phase == 0 ? &tmap_b0 : phase == 1 ? &tmap_b1 : phase == 2 ? &tmap_b2 : &tmap_b3);
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const CUtensorMap* tb_map = phase == 0 ? &tmap_b0 : phase == 1 ? &tmap_b1 : phase == 2 ? &tmap_b2 : &tmap_b3;
+      const TcChunk* chunks = p.chunks + p.chunk_begin[phase];
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t par = (it / kStages) & 1;
+        mbar_wait(empty_bar(s), par ^ 1);
+        mbar_expect_tx(full_bar(s), kStageBytes);
+        const int ci = c_begin + it;
+        const TcChunk ch = chunks[ci];
+        const uint32_t a_dst = smem_base + s * kStageBytes;
+        tma_load_5d(a_dst, &tmap_a, full_bar(s), ch.c_inner, tw * p.bw + ch.dw, ch.ph, th * p.bh + ch.dh,
+                    tb * p.nb);
+        tma_load_2d(a_dst + kABytes, tb_map, full_bar(s), ci * p.block_k, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<kTf32, kBlockN>();
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t par = (it / kStages) & 1;
+        mbar_wait(full_bar(s), par);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * kStageBytes;
+        const uint64_t da = make_smem_desc<kSwz>(a_addr);
+        const uint64_t db = make_smem_desc<kSwz>(a_addr + kABytes);
+#pragma unroll
+        for (int k = 0; k < kMmaPerChunk; ++k) {
+          // advance 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+          umma<kTf32>(tmem_base, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);             // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int r = 32 * q + lane;
+    const int iw = r % p.bw;
+    const int ih = (r / p.bw) % p.bh;
+    const int ib = r / (p.bw * p.bh);
+    const int gx = tw * p.bw + iw, gy = th * p.bh + ih, b = tb * p.nb + ib;
+    const bool valid = b < p.batch;
+    if (n_iter > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
+    if (p.split_k == 1) {
+      const int oy = gy * p.out_scale + p.py[phase], ox = gx * p.out_scale + p.px[phase];
+      OutT* dst = reinterpret_cast<OutT*>(p.out) +
+                  ((static_cast<size_t>(b) * p.hout + oy) * p.wout + ox) * p.out_pitch + p.out_coff + n0;
+#pragma unroll 1
+      for (int c = 0; c < kBlockN; c += 16) {
+        uint32_t v[16];
+        float f[16];
+        if (n_iter > 0) {
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = tc_act(__uint_as_float(v[i]) + __ldg(&p.bias[n0 + c + i]), p.act);
+        if (valid) store16(dst + c, f);
+      }
+    } else {
+      float* dst = p.partial +
+                   (static_cast<size_t>(blockIdx.z) * p.m_pad + static_cast<size_t>(blockIdx.x) * 128 + r) * p.cout + n0;
+#pragma unroll 1
+      for (int c = 0; c < kBlockN; c += 16) {
+        uint32_t v[16];
+        float f[16];
+        if (n_iter > 0) {
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        store16(dst + c, f);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// Deterministic split-K reduction + bias + activation + channel-offset store.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const TcParams p) {
+  const int cg_n = p.cout >> 2;
+  const size_t total = static_cast<size_t>(p.n_phases) * p.m_pad * cg_n;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx % cg_n);
+  const int m = static_cast<int>((idx / cg_n) % p.m_pad);
+  const int phase = static_cast<int>(idx / (static_cast<size_t>(cg_n) * p.m_pad));
+  const int tile = m >> 7, r = m & 127;
+  const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, tb = tile / (p.ntw * p.nth);
+  const int iw = r % p.bw, ih = (r / p.bw) % p.bh, ib = r / (p.bw * p.bh);
+  const int gx = tw * p.bw + iw, gy = th * p.bh + ih, b = tb * p.nb + ib;
+  if (b >= p.batch) return;
+  const int n = cg * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < p.split_k; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(
+        p.partial + (static_cast<size_t>(phase * p.split_k + s) * p.m_pad + m) * p.cout + n);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const float o[4] = {tc_act(acc.x + p.bias[n], p.act), tc_act(acc.y + p.bias[n + 1], p.act),
+                      tc_act(acc.z + p.bias[n + 2], p.act), tc_act(acc.w + p.bias[n + 3], p.act)};
+  const int oy = gy * p.out_scale + p.py[phase], ox = gx * p.out_scale + p.px[phase];
+  OutT* dst = reinterpret_cast<OutT*>(p.out) +
+              ((static_cast<size_t>(b) * p.hout + oy) * p.wout + ox) * p.out_pitch + p.out_coff + n;
+  if constexpr (sizeof(OutT) == 2) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&c);
+    *reinterpret_cast<uint2*>(dst) = u;
+  } else {
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// [tap][ci][co] fp32 (BN folded) -> [co][K] K-major in chunk order, bf16 or fp32
+template <typename E>
+__global__ void tc_pack_weights_kernel(const float* __restrict__ w_fold, int cin, int cout,
+                                       const int2* __restrict__ chunk_src, int n_chunks, int bk,
+                                       E* __restrict__ out) {
+  const int k_total = n_chunks * bk;
+  const size_t total = static_cast<size_t>(cout) * k_total;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / k_total);
+    const int k = static_cast<int>(i % k_total);
+    const int2 src = chunk_src[k / bk];
+    const float v = w_fold[(static_cast<size_t>(src.x) * cin + src.y + (k % bk)) * cout + n];
+    if constexpr (sizeof(E) == 2) out[i] = __float2bfloat16_rn(v);
+    else out[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+static PFN_cuTensorMapEncodeTiled get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, bool tf32, int rank, void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box, int swz) {
+  PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
+  if (!fn) return fail(SVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base,
+                  dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SVS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return SVS_OK;
+}
+
+static int make_tmap_a(const TcLayer& t, const LayerGeom& g, void* buf, int batch, int es, bool tf32,
+                       CUtensorMap* out) {
+  const cuuint64_t ct = kBufGeom[g.in_buf].c;
+  const cuuint64_t H = g.hin, W = g.win;
+  cuuint64_t dims[5], strides[4];
+  if (!g.transposed) {
+    dims[0] = 2 * ct; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = batch;
+    strides[0] = 2 * ct * es; strides[1] = W * ct * es; strides[2] = 2 * W * ct * es; strides[3] = H * W * ct * es;
+  } else {
+    dims[0] = ct; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = batch;
+    strides[0] = ct * es; strides[1] = W * ct * es; strides[2] = W * ct * es; strides[3] = H * W * ct * es;
+  }
+  const cuuint32_t box[5] = {static_cast<cuuint32_t>(t.block_k), static_cast<cuuint32_t>(t.bw), 1,
+                             static_cast<cuuint32_t>(t.bh), static_cast<cuuint32_t>(t.nb)};
+  return encode_map(out, tf32, 5, buf, dims, strides, box, t.swz);
+}
+
+static unsigned tc_disable_mask() {
+  const char* e = std::getenv("SVS_TC_DISABLE_MASK");   // debugging: bit li set -> layer li on the CUDA-core path
+  return e ? static_cast<unsigned>(std::strtoul(e, nullptr, 0)) : 0u;
+}
+
+int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
+  const bool tf32 = plan->precision == SVS_PRECISION_TF32;
+  const int es = plan->elem_size;
+  const unsigned disable = tc_disable_mask();
+  for (int li = 1; li <= 10; ++li) {
+    const LayerGeom& g = kLayers[li];
+    TcLayer& t = plan->tc[li];
+    t.layer = li;
+    int swz = g.cin * es >= 128 ? 128 : g.cin * es;     // one swizzle row = min(128 B, all input channels)
+    if (swz < 32 || (disable >> li) & 1u) continue;     // conv2 in bf16 would be 32-byte rows: allowed
+    t.swz = swz;
+    t.block_k = swz / es;
+    t.block_n = g.cout < 128 ? g.cout : 128;
+    t.gw = g.transposed ? g.win : g.wout;
+    t.gh = g.transposed ? g.hin : g.hout;
+    t.bw = t.gw < 16 ? t.gw : 16;
+    t.bh = t.gh < 128 / t.bw ? t.gh : 128 / t.bw;
+    t.nb = 128 / (t.bw * t.bh);
+    // ---- K-chunk schedule ----
+    std::vector<int2> src;
+    const int ct = kBufGeom[g.in_buf].c;
+    t.chunks.clear();
+    if (!g.transposed) {
+      t.n_phases = 1;
+      t.phases[0] = TcPhase{0, 0, 0, 0, 0};
+      for (int kh = 0; kh < 5; ++kh)
+        for (int kw = 0; kw < 5; ++kw) {
+          const int qh = kh - 2, qw = kw - 2;
+          const int ph = qh & 1, pw = qw & 1;
+          const int dh = (qh - ph) / 2, dw = (qw - pw) / 2;
+          for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
+            t.chunks.push_back(TcChunk{pw * ct + g.in_coff + c0, dw, ph, dh});
+            src.push_back(make_int2(kh * 5 + kw, c0));
+          }
+        }
+      t.phases[0].n_chunks = static_cast<int>(t.chunks.size());
+    } else {
+      t.n_phases = 4;
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          TcPhase& phs = t.phases[py * 2 + px];
+          phs.py = py; phs.px = px;
+          phs.chunk_begin = static_cast<int>(t.chunks.size());
+          for (int kh = py; kh < 5; kh += 2)
+            for (int kw = px; kw < 5; kw += 2) {
+              const int dh = (py + 2 - kh) / 2, dw = (px + 2 - kw) / 2;
+              for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
+                t.chunks.push_back(TcChunk{g.in_coff + c0, dw, 0, dh});
+                src.push_back(make_int2(kh * 5 + kw, c0));
+              }
+            }
+          phs.n_chunks = static_cast<int>(t.chunks.size()) - phs.chunk_begin;
+        }
+    }
+    // ---- upload schedule, pack weights ----
+    const size_t n_chunks_total = t.chunks.size();
+    int2* d_src = nullptr;
+    SVS_CUDA_TRY(cudaMalloc(&t.d_chunks, sizeof(TcChunk) * n_chunks_total));
+    SVS_CUDA_TRY(cudaMalloc(&d_src, sizeof(int2) * n_chunks_total));
+    SVS_CUDA_TRY(cudaMemcpyAsync(t.d_chunks, t.chunks.data(), sizeof(TcChunk) * n_chunks_total,
+                                 cudaMemcpyHostToDevice, st));
+    SVS_CUDA_TRY(cudaMemcpyAsync(d_src, src.data(), sizeof(int2) * n_chunks_total, cudaMemcpyHostToDevice, st));
+    const size_t w_elems = n_chunks_total * t.block_k * g.cout;
+    SVS_CUDA_TRY(cudaMalloc(&t.d_weights, w_elems * es));
+    size_t off = 0;
+    for (int ph = 0; ph < t.n_phases; ++ph) {
+      TcPhase& phs = t.phases[ph];
+      phs.b_elem_off = static_cast<int64_t>(off);
+      t.k_total[ph] = phs.n_chunks * t.block_k;
+      const size_t n = static_cast<size_t>(g.cout) * t.k_total[ph];
+      const unsigned blocks = static_cast<unsigned>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+      if (tf32)
+        tc_pack_weights_kernel<float><<<blocks, 256, 0, st>>>(plan->w_fold[li], g.cin, g.cout,
+                                                             d_src + phs.chunk_begin, phs.n_chunks, t.block_k,
+                                                             static_cast<float*>(t.d_weights) + off);
+      else
+        tc_pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+            plan->w_fold[li], g.cin, g.cout, d_src + phs.chunk_begin, phs.n_chunks, t.block_k,
+            static_cast<__nv_bfloat16*>(t.d_weights) + off);
+      SVS_CHECK_LAUNCH("tc_pack_weights_kernel");
+      // B tensor map: [Cout][K] K-major
+      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(t.k_total[ph]), static_cast<cuuint64_t>(g.cout)};
+      const cuuint64_t strides[1] = {static_cast<cuuint64_t>(t.k_total[ph]) * es};
+      const cuuint32_t box[2] = {static_cast<cuuint32_t>(t.block_k), static_cast<cuuint32_t>(t.block_n)};
+      int rc = encode_map(&t.tmap_b[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides, box,
+                          t.swz);
+      if (rc != SVS_OK) return rc;
+      off += n;
+    }
+    for (int ph = t.n_phases; ph < 4; ++ph) t.tmap_b[ph] = t.tmap_b[0];
+    SVS_CUDA_TRY(cudaStreamSynchronize(st));     // d_src / host vectors are consumed
+    SVS_CUDA_TRY(cudaFree(d_src));
+    t.enabled = true;
+  }
+  return SVS_OK;
+}
+
+void tc_free_layers(svs_unet_plan* plan) {
+  for (int li = 0; li < 12; ++li) {
+    TcLayer& t = plan->tc[li];
+    if (t.d_chunks) cudaFree(t.d_chunks);
+    if (t.d_weights) cudaFree(t.d_weights);
+    t.d_chunks = nullptr; t.d_weights = nullptr; t.enabled = false;
+  }
+}
+
+void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, int* split_k) {
+  const int ntw = t.gw / t.bw, nth = t.gh / t.bh, ntb = (batch + t.nb - 1) / t.nb;
+  *m_tiles = ntw * nth * ntb;
+  const int n_tiles = g.cout / t.block_n;
+  const int tiles = *m_tiles * n_tiles * t.n_phases;
+  int min_chunks = 1 << 30;
+  for (int ph = 0; ph < t.n_phases; ++ph) min_chunks = t.phases[ph].n_chunks < min_chunks ? t.phases[ph].n_chunks : min_chunks;
+  int s = 1;
+  const char* e = std::getenv("SVS_TC_SPLITK");
+  if (e) s = std::atoi(e);
+  else if (tiles < 120) s = 148 / tiles;
+  if (s > 8) s = 8;
+  if (s > min_chunks / 4) s = min_chunks / 4;
+  if (s < 1) s = 1;
+  *split_k = s;
+}
+
+size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch) {
+  size_t best = 0;
+  for (int li = 0; li < 12; ++li) {
+    const TcLayer& t = plan->tc[li];
+    if (!t.enabled) continue;
+    int m_tiles, split;
+    tc_tiling(t, kLayers[li], batch, &m_tiles, &split);
+    if (split > 1) {
+      const size_t bytes = static_cast<size_t>(split) * t.n_phases * m_tiles * 128 * kLayers[li].cout * sizeof(float);
+      best = bytes > best ? bytes : best;
+    }
+  }
+  return best;
+}
+
+int tc_launch_count(const svs_unet_plan* plan, int li, int batch) {
+  int m_tiles, split;
+  tc_tiling(plan->tc[li], kLayers[li], batch, &m_tiles, &split);
+  return split > 1 ? 2 : 1;   // main kernel (+ split-K reduction)
+}
+
+template <typename OutT, bool kTf32, int kBlockN, int kSwz, int kStages>
+static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = tc_conv_kernel<OutT, kTf32, kBlockN, kSwz, kStages>;
+  constexpr size_t smem = tc_smem_bytes<kBlockN, kSwz, kStages>();
+  SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<grid, kTcThreads, smem, st>>>(ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2], t.tmap_b[3], p);
+  SVS_CHECK_LAUNCH("tc_conv_kernel");
+  return SVS_OK;
+}
+
+int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st) {
+  const TcLayer& t = plan->tc[li];
+  const LayerGeom& g = kLayers[li];
+  const bool tf32 = plan->precision == SVS_PRECISION_TF32;
+  const int es = plan->elem_size;
+  static std::mutex mu;
+  CUtensorMap ta;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (t.tmap_a_base != ws.buf[g.in_buf] || t.tmap_a_batch != batch) {
+      int rc = make_tmap_a(t, g, ws.buf[g.in_buf], batch, es, tf32, &t.tmap_a);
+      if (rc != SVS_OK) return rc;
+      t.tmap_a_base = ws.buf[g.in_buf];
+      t.tmap_a_batch = batch;
+    }
+    ta = t.tmap_a;
+  }
+  TcParams p{};
+  p.chunks = t.d_chunks;
+  for (int ph = 0; ph < 4; ++ph) {
+    p.n_chunks[ph] = t.phases[ph < t.n_phases ? ph : 0].n_chunks;
+    p.chunk_begin[ph] = t.phases[ph < t.n_phases ? ph : 0].chunk_begin;
+    p.py[ph] = t.phases[ph < t.n_phases ? ph : 0].py;
+    p.px[ph] = t.phases[ph < t.n_phases ? ph : 0].px;
+  }
+  int m_tiles, split;
+  tc_tiling(t, g, batch, &m_tiles, &split);
+  p.n_phases = t.n_phases;
+  p.split_k = split;
+  p.ntw = t.gw / t.bw; p.nth = t.gh / t.bh;
+  p.bw = t.bw; p.bh = t.bh; p.nb = t.nb;
+  p.batch = batch;
+  p.block_k = t.block_k;
+  p.out = ws.buf[g.out_buf];
+  p.out_pitch = kBufGeom[g.out_buf].c;
+  p.out_coff = g.out_coff;
+  p.hout = g.hout; p.wout = g.wout;
+  p.out_scale = g.transposed ? 2 : 1;
+  p.bias = plan->b_fold[li];
+  p.act = g.act;
+  p.partial = ws.splitk;
+  p.m_pad = m_tiles * 128;
+  p.cout = g.cout;
+  if (split > 1 && ws.splitk_bytes < static_cast<size_t>(split) * t.n_phases * p.m_pad * g.cout * sizeof(float))
+    return fail(SVS_ERR_WORKSPACE, "tc_launch_layer: split-K scratch too small");
+  dim3 grid(m_tiles, g.cout / t.block_n, t.n_phases * split);
+  int rc = SVS_ERR_NOT_IMPLEMENTED;
+#define SVS_TC_CASE(N, S, ST)                                                                       \
+  if (t.block_n == N && t.swz == S) {                                                               \
+    rc = tf32 ? launch_tc<float, true, N, S, ST>(ta, t, p, grid, st)                                \
+              : launch_tc<__nv_bfloat16, false, N, S, ST>(ta, t, p, grid, st);                      \
+  }
+  SVS_TC_CASE(128, 128, 3)
+  SVS_TC_CASE(64, 128, 4)
+  SVS_TC_CASE(32, 128, 4)
+  SVS_TC_CASE(16, 128, 4)
+  SVS_TC_CASE(64, 64, 4)
+  SVS_TC_CASE(32, 64, 4)
+  SVS_TC_CASE(32, 32, 4)
+#undef SVS_TC_CASE
+  if (rc == SVS_ERR_NOT_IMPLEMENTED)
+    return fail(rc, "tc_launch_layer: no kernel instantiation for block_n=" + std::to_string(t.block_n) +
+                        " swz=" + std::to_string(t.swz));
+  if (rc != SVS_OK) return rc;
+  if (split > 1) {
+    const size_t total = static_cast<size_t>(t.n_phases) * p.m_pad * (g.cout / 4);
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    if (tf32) splitk_finish_kernel<float><<<blocks, 256, 0, st>>>(p);
+    else splitk_finish_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+    SVS_CHECK_LAUNCH("splitk_finish_kernel");
+  }
+  return SVS_OK;
+}
+
+}  // namespace svs

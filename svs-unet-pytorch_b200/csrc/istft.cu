@@ -1,0 +1,191 @@
+// K2: batched inverse STFT with deterministic gather-form overlap-add for sm_100a.
+//
+// Replaces `librosa.istft(mag * phase, win_length=1024, hop_length=768)` (reference data.py:159)
+// and the peak search of data.py:162: complex recombine fused into the load, inverse real FFT via
+// the 512-point complex transform of fft512.cuh, Hann window, then each OUTPUT sample gathers the
+// (at most two) frames covering it and divides by the window-sum-of-squares envelope.  There are
+// no atomics on the waveform, so the result is bit-reproducible.
+//
+// With padded position P = p + 512:  frame t covers P in [768 t, 768 t + 1024).  Segment t =
+// [768 t, 768 t + 768) receives frame t (offset r = P - 768 t) and, for r < 256, frame t-1
+// (offset r + 768).  A CTA owns kSeg consecutive segments of one song and transforms kSeg + 1
+// frames (the first one only for its tail), i.e. 1/kSeg redundant transforms and no inter-CTA
+// dependency.
+#include "svs_common.cuh"
+#include "fft512.cuh"
+
+namespace svs {
+
+constexpr int kIstftThreads = 256;
+constexpr int kIstftFrames = 16;                 // frames transformed per CTA (4 rounds of 4 groups)
+constexpr int kIstftSeg = kIstftFrames - 1;      // output segments per CTA
+constexpr int kFramePitch = 1024;
+constexpr size_t kIstftSmemBytes =
+    sizeof(float) * (kIstftFrames * kFramePitch + 4 * kFftGroupFloats);
+
+__global__ void __launch_bounds__(kIstftThreads)
+istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase,
+                 const int64_t* __restrict__ frame_off, const int64_t* __restrict__ wave_off,
+                 float* __restrict__ wave, float* __restrict__ song_peak,
+                 const float2* __restrict__ tw1024, const float* __restrict__ hann,
+                 const float* __restrict__ env_both, const float* __restrict__ env_single) {
+  extern __shared__ float smem[];
+  float* frames = smem;                                     // [kIstftFrames][1024] windowed frames
+  float* scratch_all = smem + kIstftFrames * kFramePitch;
+
+  const int song = blockIdx.y;
+  const int64_t f0 = frame_off[song];
+  const int n_frames = static_cast<int>(frame_off[song + 1] - f0);
+  const int seg_begin = blockIdx.x * kIstftSeg;             // first segment (= frame index) of the CTA
+  if (seg_begin >= n_frames) return;
+  const int group = threadIdx.x >> 6;
+  const int j = threadIdx.x & 63;
+  float* scratch = scratch_all + group * kFftGroupFloats;
+  float* xre = scratch;
+  float* xim = scratch + kFftScratchFloats;
+  const int bar = 1 + group;
+
+  FftTwiddles tw;
+  load_fft_twiddles(tw, tw1024, j);
+  float2 twp[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) twp[q] = __ldg(&tw1024[j + 64 * q]);
+
+  // ---- transform frames seg_begin-1 .. seg_begin+kIstftSeg-1 into `frames` ----
+  for (int slot = group; slot < kIstftFrames; slot += 4) {
+    const int t = seg_begin - 1 + slot;
+    float* fr = frames + slot * kFramePitch;
+    if (t < 0 || t >= n_frames) {                           // uniform per group
+      for (int i = j; i < kFramePitch; i += 64) fr[i] = 0.0f;
+      continue;
+    }
+    const float* __restrict__ mrow = mag + (f0 + t) * SVS_N_BINS;
+    const float2* __restrict__ prow = phase + (f0 + t) * SVS_N_BINS;
+    // Z[k] = E[k] + i O[k],  E = (X[k] + conj X[512-k])/2,  O = (X[k] - conj X[512-k])/2 * conj(W^k);
+    // the inverse transform is conj(FFT(conj Z)), so conj(Z) is what goes into the exchange buffer.
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      if (q == 4 && j != 0) break;
+      const int k = j + 64 * q;
+      const int kk = 512 - k;
+      const float mk = __ldg(&mrow[k]), mkk = __ldg(&mrow[kk]);
+      const float2 pk = __ldg(&prow[k]), pkk = __ldg(&prow[kk]);
+      float2 xk = make_float2(mk * pk.x, mk * pk.y);         // data.py:159  mag * phase
+      float2 xkk = make_float2(mkk * pkk.x, mkk * pkk.y);
+      if (k == 0) { xk.y = 0.0f; xkk.y = 0.0f; }             // c2r ignores Im of DC and Nyquist
+      const float2 e = make_float2(0.5f * (xk.x + xkk.x), 0.5f * (xk.y - xkk.y));
+      const float2 dd = make_float2(0.5f * (xk.x - xkk.x), 0.5f * (xk.y + xkk.y));
+      const float2 w = (q < 4) ? twp[q & 3] : make_float2(0.0f, -1.0f);
+      const float2 o = cmul(dd, cconj(w));
+      // Z[k] = E + iO -> conj: (E.x - O.y, -(E.y + O.x)) ; Z[512-k] = conj(E) + i conj(O)
+      const int ak = z_addr(k & 511);
+      xre[ak] = e.x - o.y; xim[ak] = -(e.y + o.x);
+      if (kk < 512 && kk != k) {
+        const int akk = z_addr(kk);
+        xre[akk] = e.x + o.y; xim[akk] = -(o.x - e.y);
+      }
+    }
+    group_bar(bar);
+    float2 v[8];
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) {
+      const int a = z_addr(j + 64 * n1);
+      v[n1] = make_float2(xre[a], xim[a]);
+    }
+    group_bar(bar);                                          // pass A rewrites buffer X
+    fft512_group(v, tw, scratch, j, bar);
+    // v[d] = FFT(conj Z)[n], n = jj + 64 d ;  z[n] = conj(v)/512 ;  x[2n] = Re, x[2n+1] = Im
+    const int jj = (j >> 3) + 8 * (j & 7);
+    const float sc = 1.0f / 512.0f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const int n = jj + 64 * d;
+      const float2 wv = make_float2(__ldg(&hann[2 * n]), __ldg(&hann[2 * n + 1]));
+      *reinterpret_cast<float2*>(&fr[2 * n]) = make_float2(v[d].x * sc * wv.x, -v[d].y * sc * wv.y);
+    }
+    group_bar(bar);                                          // buffers reused by this group's next frame
+  }
+  __syncthreads();
+
+  // ---- gather-form overlap-add: every output sample is written exactly once ----
+  const int64_t w0 = wave_off[song];
+  const int out_len = SVS_HOP * (n_frames - 1);             // librosa: hop * (T - 1) after trimming
+  float peak = 0.0f;
+  const int n_seg = min(kIstftSeg, n_frames - seg_begin);
+  for (int i = threadIdx.x; i < n_seg * SVS_HOP; i += kIstftThreads) {
+    const int s = i / SVS_HOP;
+    const int r = i - s * SVS_HOP;
+    const int t = seg_begin + s;
+    const int p = t * SVS_HOP + r - SVS_N_FFT / 2;          // output sample index
+    if (p < 0 || p >= out_len) continue;
+    const float cur = frames[(s + 1) * kFramePitch + r];
+    float val, env;
+    if (r < SVS_N_FFT - SVS_HOP && t > 0) {
+      val = frames[s * kFramePitch + r + SVS_HOP] + cur;    // frame t-1 was added first, then frame t
+      env = __ldg(&env_both[r]);
+    } else {
+      val = cur;
+      env = __ldg(&env_single[r]);
+    }
+    if (env > 1.17549435e-38f) val = val / env;              // librosa: where env > tiny(float32)
+    wave[w0 + p] = val;
+    peak = fmaxf(peak, fabsf(val));
+  }
+  if (song_peak != nullptr) {
+    peak = warp_max(peak);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(&song_peak[song], peak);
+  }
+}
+
+__global__ void wave_peak_normalize_kernel(float* __restrict__ wave, const int64_t* __restrict__ wave_off,
+                                           const float* __restrict__ song_peak, int n_songs,
+                                           int64_t total, float target) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int lo = 0, hi = n_songs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (wave_off[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const float pk = song_peak[lo];
+    if (pk > 0.0f) wave[i] = wave[i] / pk * target;          // reference data.py:163-164
+  }
+}
+
+}  // namespace svs
+
+extern "C" int svs_istft_ola(const float* mag, const float* phase, const int64_t* frame_off,
+                             const int64_t* wave_off, int n_songs, int64_t max_frames, float* wave,
+                             float* song_peak, void* stream) {
+  using namespace svs;
+  SVS_REQUIRE(mag && phase && frame_off && wave_off && wave, "svs_istft_ola: null pointer");
+  SVS_REQUIRE(n_songs > 0 && n_songs <= 65535, "svs_istft_ola: n_songs must be in [1, 65535]");
+  SVS_REQUIRE(max_frames > 0, "svs_istft_ola: max_frames must be positive");
+  SpectralTables tabs;
+  int rc = get_spectral_tables(&tabs);
+  if (rc != SVS_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SVS_CUDA_TRY(cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kIstftSmemBytes)));
+  if (song_peak) SVS_CUDA_TRY(cudaMemsetAsync(song_peak, 0, sizeof(float) * n_songs, st));
+  dim3 grid(static_cast<unsigned>((max_frames + kIstftSeg - 1) / kIstftSeg), n_songs);
+  istft_ola_kernel<<<grid, kIstftThreads, kIstftSmemBytes, st>>>(
+      mag, reinterpret_cast<const float2*>(phase), frame_off, wave_off, wave, song_peak, tabs.tw1024,
+      tabs.hann, tabs.env_both, tabs.env_single);
+  SVS_CHECK_LAUNCH("istft_ola_kernel");
+  return SVS_OK;
+}
+
+extern "C" int svs_wave_peak_normalize(float* wave, const int64_t* wave_off, const float* song_peak,
+                                       int n_songs, int64_t total_samples, float target, void* stream) {
+  using namespace svs;
+  SVS_REQUIRE(wave && wave_off && song_peak, "svs_wave_peak_normalize: null pointer");
+  SVS_REQUIRE(n_songs > 0 && total_samples >= 0, "svs_wave_peak_normalize: bad sizes");
+  if (total_samples == 0) return SVS_OK;
+  int64_t blocks = (total_samples + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  wave_peak_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      wave, wave_off, song_peak, n_songs, total_samples, target);
+  SVS_CHECK_LAUNCH("wave_peak_normalize_kernel");
+  return SVS_OK;
+}

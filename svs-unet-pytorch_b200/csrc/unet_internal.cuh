@@ -1,0 +1,103 @@
+// Internal description of the UNet layers, the activation workspace and the plan object.
+#pragma once
+#include "svs_common.cuh"
+#include <cuda.h>
+#include <vector>
+
+namespace svs {
+
+enum Act { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
+
+// Activation buffers inside the workspace.  Every decoder input is a "concat buffer"
+// [B][H][W][2C] whose first C channels are written by the previous decoder layer and whose last C
+// channels are written by the matching encoder layer (torch.cat([deconv_out, conv_skip], 1) of
+// reference model.py:186-198 realised as channel-offset stores).
+enum Buf { BUF_CAT1 = 0, BUF_CAT2, BUF_CAT3, BUF_CAT4, BUF_CAT5, BUF_X6, BUF_COUNT };
+
+struct BufGeom { int h, w, c; };
+// H = frequency bins, W = frames, C = channel pitch.
+static const BufGeom kBufGeom[BUF_COUNT] = {
+    {256, 64, 32}, {128, 32, 64}, {64, 16, 128}, {32, 8, 256}, {16, 4, 512}, {8, 2, 512}};
+
+struct LayerGeom {
+  bool transposed;
+  int cin, cout;
+  int hin, win, hout, wout;
+  int in_buf, in_coff;     // in_buf < 0: external patch view (conv1)
+  int out_buf, out_coff;   // out_buf < 0: external patch view (deconv6)
+  int act;
+};
+// layers[0..5] = conv1..conv6, layers[6..11] = deconv1..deconv6
+static const LayerGeom kLayers[12] = {
+    {false, 1, 16, 512, 128, 256, 64, -1, 0, BUF_CAT1, 16, ACT_LEAKY},
+    {false, 16, 32, 256, 64, 128, 32, BUF_CAT1, 16, BUF_CAT2, 32, ACT_LEAKY},
+    {false, 32, 64, 128, 32, 64, 16, BUF_CAT2, 32, BUF_CAT3, 64, ACT_LEAKY},
+    {false, 64, 128, 64, 16, 32, 8, BUF_CAT3, 64, BUF_CAT4, 128, ACT_LEAKY},
+    {false, 128, 256, 32, 8, 16, 4, BUF_CAT4, 128, BUF_CAT5, 256, ACT_LEAKY},
+    {false, 256, 512, 16, 4, 8, 2, BUF_CAT5, 256, BUF_X6, 0, ACT_LEAKY},
+    {true, 512, 256, 8, 2, 16, 4, BUF_X6, 0, BUF_CAT5, 0, ACT_RELU},
+    {true, 512, 128, 16, 4, 32, 8, BUF_CAT5, 0, BUF_CAT4, 0, ACT_RELU},
+    {true, 256, 64, 32, 8, 64, 16, BUF_CAT4, 0, BUF_CAT3, 0, ACT_RELU},
+    {true, 128, 32, 64, 16, 128, 32, BUF_CAT3, 0, BUF_CAT2, 0, ACT_RELU},
+    {true, 64, 16, 128, 32, 256, 64, BUF_CAT2, 0, BUF_CAT1, 0, ACT_RELU},
+    {true, 32, 1, 256, 64, 512, 128, BUF_CAT1, 0, -1, 0, ACT_NONE},
+};
+
+constexpr int kBatchPad = 8;      // workspace batch is padded to a multiple of 8 (deep-layer M tiles)
+inline int padded_batch(int b) { return (b + kBatchPad - 1) / kBatchPad * kBatchPad; }
+
+struct Workspace {
+  char* buf[BUF_COUNT];
+  float* splitk;            // fp32 partial accumulators for split-K layers
+  size_t splitk_bytes;
+  size_t total_bytes;
+};
+// Carves `base` (may be nullptr to only compute sizes) for `batch` patches of element size `es`.
+Workspace carve_workspace(char* base, int batch, int es, size_t splitk_bytes);
+
+// ---- tensor-core (tcgen05) layer plan --------------------------------------------------------
+struct TcChunk {            // one K-chunk of the implicit GEMM: which input slab feeds the MMA
+  int c_inner;              // coordinate in the innermost (channel / parity-merged channel) dimension
+  int dw;                   // offset added to the tile's w coordinate
+  int ph;                   // coordinate in the row-parity dimension (conv) or 0 (deconv)
+  int dh;                   // offset added to the tile's h coordinate
+};
+
+struct TcPhase {
+  int n_chunks;
+  int chunk_begin;          // into TcLayer::chunks
+  int py, px;               // output sub-pixel phase (deconv) or 0
+  int64_t b_elem_off;       // element offset of this phase's [Cout][K] weight matrix
+};
+
+struct TcLayer {
+  bool enabled = false;
+  int layer = -1;
+  int bw = 0, bh = 0, nb = 0;        // M tile = bw x bh x nb = 128 pixels
+  int gw = 0, gh = 0;                // pixel grid the M index runs over (conv: output, deconv: input)
+  int block_n = 0;                   // N tile
+  int swz = 128;                     // bytes of K per smem row == TMA/UMMA swizzle span (32/64/128)
+  int block_k = 0;                   // K elements per chunk = swz / elem_size
+  int n_phases = 1;
+  TcPhase phases[4];
+  std::vector<TcChunk> chunks;       // host copy
+  TcChunk* d_chunks = nullptr;       // device copy
+  void* d_weights = nullptr;         // packed [phase][Cout][K] K-major (bf16 or fp32/tf32)
+  int k_total[4] = {0, 0, 0, 0};
+  CUtensorMap tmap_b[4];             // per phase, 2-D [Cout][K]
+  // A-operand tensor map depends on (workspace, batch): cached for the last pair seen
+  mutable CUtensorMap tmap_a;
+  mutable const void* tmap_a_base = nullptr;
+  mutable int tmap_a_batch = -1;
+};
+
+}  // namespace svs
+
+struct svs_unet_plan {
+  int precision = SVS_PRECISION_FP32;
+  int elem_size = 4;
+  int device = 0;
+  float* w_fold[12] = {};            // folded fp32 weights [25][Cin][Cout]
+  float* b_fold[12] = {};            // folded fp32 bias [Cout]
+  svs::TcLayer tc[12];
+};

@@ -1,0 +1,73 @@
+"""CPU: the librosa-0.10.1 restatement (oracle/stft_oracle.py) against torch.stft / torch.istft in
+float64 (an independent statement of the same transforms) and the structural facts of SURVEY.md section 4.
+PARITY UNPINNED at the librosa boundary: the reference ships no vectors for this half."""
+import numpy as np
+import torch
+
+from oracle import stft_oracle as so
+from svs_unet_pytorch_b200 import synth
+
+
+def _torch_stft64(y):
+    w = torch.hann_window(1024, periodic=True, dtype=torch.float64)
+    return torch.stft(torch.from_numpy(y).double(), n_fft=1024, hop_length=768, window=w, center=True,
+                      pad_mode="constant", return_complex=True).numpy()
+
+
+def test_known_shapes():
+    assert so.n_frames(245760) == 321 and so.n_frames(1474560) == 1921
+    y = np.zeros(245760, dtype=np.float32)
+    d = so.stft(y)
+    assert d.shape == (513, 321) and d.dtype == np.complex64 and d.flags["F_CONTIGUOUS"]
+
+
+def test_stft_matches_torch_float64():
+    mix, _, _ = synth.synth_song(5.0, seed=1234)
+    d = so.stft(mix)
+    ref = _torch_stft64(mix)
+    assert d.shape == ref.shape
+    assert np.abs(d - ref.astype(np.complex64)).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_magphase_zero_rule():
+    d = np.array([[0 + 0j, 3 + 4j], [1e-30 + 0j, -2j]], dtype=np.complex64)
+    mag, ph = so.magphase(d)
+    assert mag.dtype == np.float32 and ph.dtype == np.complex64
+    assert ph[0, 0] == 1 + 0j and np.allclose(ph[0, 1], 0.6 + 0.8j) and np.allclose(ph[1, 1], -1j)
+    assert np.allclose(np.abs(ph), 1.0)
+
+
+def test_to_spec_normalises_by_mixture_max():
+    mix, voc, _ = synth.synth_song(3.0, seed=7)
+    spec_m, ph_m, norm = so.to_spec(mix)
+    spec_v, _, norm_v = so.to_spec(mix, voc)
+    assert spec_m.max() == np.float32(1.0) and norm == norm_v
+    assert spec_v.max() < 1.0 + 1e-6
+    z, _, n0 = so.to_spec(np.zeros(4096, dtype=np.float32))
+    assert n0 == 1 and np.all(z == 0)
+
+
+def test_istft_matches_torch_and_round_trips():
+    rng = np.random.default_rng(0)
+    y = (0.1 * rng.standard_normal(768 * 40)).astype(np.float32)
+    d = so.stft(y)
+    yr = so.istft(d)
+    assert yr.dtype == np.float32 and yr.shape[0] == 768 * (d.shape[1] - 1) == len(y)
+    assert np.abs(yr - y).max() < 1e-6
+    w = torch.hann_window(1024, periodic=True, dtype=torch.float64)
+    ref = torch.istft(torch.from_numpy(d.astype(np.complex128)), n_fft=1024, hop_length=768, window=w,
+                      center=True, length=len(y)).numpy()
+    assert np.abs(yr - ref).max() < 1e-6
+
+
+def test_envelope_never_zero_after_trim():
+    env = so.window_sumsquare(10)[512:512 + 768 * 9]
+    assert env.min() > 0.04 and env.max() <= 1.0 + 1e-6
+
+
+def test_to_wave_peak_normalises():
+    mix, _, _ = synth.synth_song(3.0, seed=5)
+    spec, ph, _ = so.to_spec(mix)
+    y = so.to_wave(spec, ph)
+    assert abs(np.abs(y).max() - 0.9) < 1e-6
+    assert synth.sdr_db(mix[: len(y)], y) > 60.0
