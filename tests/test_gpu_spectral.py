@@ -1,0 +1,105 @@
+"""GPU: STFT / magphase / iSTFT kernels against the CPU oracle (oracle/stft_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import stft_oracle as so  # noqa: E402
+from svs_unet_pytorch_b200 import spectral, synth  # noqa: E402
+
+
+def _songs():
+    rng = np.random.default_rng(0)
+    out = [synth.synth_song(30.0, seed=1234)[0],                       # config 1: 245,760 samples -> 321 frames
+           (0.1 * rng.standard_normal(768 * 7 + 5)).astype(np.float32),   # ragged, len % 768 != 0
+           np.zeros(2000, dtype=np.float32),                            # silent song: norm == 0 -> 1, phase 1+0j
+           (0.5 * rng.standard_normal(700)).astype(np.float32)]        # shorter than one hop: a single frame
+    return out
+
+
+def test_stft_mag_phase_matches_oracle():
+    songs = _songs()
+    batch = spectral.SongBatch.from_audio(songs)
+    mag, phase, smax = batch.stft()
+    torch.cuda.synchronize()
+    assert batch.frames == [so.n_frames(len(s)) for s in songs]
+    for i, y in enumerate(songs):
+        d = so.stft(y)
+        rmag, rph = so.magphase(d)
+        got = batch.song_spec(mag, i).cpu().numpy()
+        assert got.shape == rmag.shape
+        scale = max(float(rmag.max()), 1e-30)
+        # north_star tolerance: STFT magnitude within 1e-4 relative (to the spectrum max, SURVEY section 4 caution i)
+        assert np.abs(got - rmag).max() <= 1e-4 * scale, (i, np.abs(got - rmag).max(), scale)
+        assert abs(float(smax[i]) - float(rmag.max())) <= 1e-4 * scale
+        a, b = int(batch.frame_off_host[i]), int(batch.frame_off_host[i + 1])
+        ph = torch.view_as_complex(phase[a:b]).cpu().numpy().T
+        assert np.allclose(np.abs(ph), 1.0, atol=1e-5)                # unit phasors (1+0j where mag == 0)
+        strong = rmag > 1e-3 * scale                                  # phase is ill-conditioned in empty bins
+        if strong.any():
+            assert np.abs(ph[strong] - rph[strong]).max() < 2e-3
+    z = batch.song_spec(mag, 2).cpu().numpy()
+    assert np.all(z == 0) and float(smax[2]) == 0.0
+    a = int(batch.frame_off_host[2])
+    assert torch.all(phase[a, :, 0] == 1.0) and torch.all(phase[a, :, 1] == 0.0)
+
+
+def test_librosa_shaped_calls():
+    y = synth.synth_song(5.0, seed=3)[0]
+    d = spectral.stft(y, n_fft=1024, hop_length=768)
+    ref = so.stft(y)
+    assert d.shape == ref.shape == (513, 54) and d.dtype == np.complex64 and d.flags["F_CONTIGUOUS"]
+    assert np.abs(d - ref).max() <= 1e-4 * np.abs(ref).max()
+    mag, ph = spectral.magphase(d)
+    rmag, rph = so.magphase(d)
+    assert mag.dtype == np.float32 and ph.dtype == np.complex64
+    assert np.abs(mag - rmag).max() <= 1e-6 * rmag.max() and np.abs(ph - rph).max() < 1e-5
+    yr = spectral.istft(ref, win_length=1024, hop_length=768)
+    ryr = so.istft(ref)
+    assert yr.shape == ryr.shape and yr.dtype == np.float32
+    assert np.abs(yr - ryr).max() < 1e-5
+    with pytest.raises(RuntimeError):
+        spectral.stft(y, n_fft=1024, hop_length=256)                  # other config.py sets are rejected
+
+
+def test_normalize_and_round_trip_batch():
+    songs = _songs()
+    batch = spectral.SongBatch.from_audio(songs)
+    mag, phase, smax = batch.stft()
+    raw = mag.clone()
+    batch.normalize(mag, smax)
+    for i in range(len(songs)):
+        n = float(smax[i]) or 1.0
+        got = batch.song_spec(mag, i).cpu().numpy()
+        exp = batch.song_spec(raw, i).cpu().numpy() / np.float32(n)    # data.py:105
+        assert np.array_equal(got, exp)
+    wave, peak = batch.istft(raw, phase)
+    wave_n = wave.clone()
+    from svs_unet_pytorch_b200 import _lib
+    _lib.wave_peak_normalize_raw(wave_n, batch.wave_off, peak, batch.n_songs, 0.9)
+    torch.cuda.synchronize()
+    for i, y in enumerate(songs):
+        got = batch.song_wave(wave, i).cpu().numpy()
+        ref = so.istft(so.stft(y))
+        assert got.shape == ref.shape
+        if len(ref):
+            assert np.abs(got - ref).max() < 2e-6 * max(1.0, np.abs(ref).max())
+            assert np.abs(got - y[: len(got)]).max() < 1e-5             # STFT -> iSTFT round trip
+            assert abs(float(peak[i]) - np.abs(ref).max()) < 1e-5
+            gn = batch.song_wave(wave_n, i).cpu().numpy()
+            if np.abs(ref).max() > 0:
+                assert abs(np.abs(gn).max() - 0.9) < 1e-5               # data.py:163-164
+
+
+def test_istft_is_bit_reproducible():
+    songs = [synth.synth_song(180.0, seed=1234 + i)[0] for i in range(2)]   # config 3 size: 1921 frames
+    batch = spectral.SongBatch.from_audio(songs)
+    mag, phase, _ = batch.stft()
+    w1, _ = batch.istft(mag, phase)
+    w2, _ = batch.istft(mag, phase)
+    assert torch.equal(w1, w2)
+    assert batch.frames == [1921, 1921] and w1.numel() == 2 * 1474560
+    for i, y in enumerate(songs):
+        got = batch.song_wave(w1, i).cpu().numpy()
+        assert np.abs(got - y).max() < 1e-5
