@@ -152,6 +152,12 @@ int svs_unet_forward(const svs_unet_plan* plan, const svs_patch_view* in, const 
                      const int32_t* in_frames, int batch, int flags, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Profiling hook: enqueue only layers [first_layer, last_layer] (0 = conv1 .. 11 = deconv6) on a
+ * workspace that already holds the inputs of `first_layer` from an earlier full forward. */
+int svs_unet_forward_layers(const svs_unet_plan* plan, const svs_patch_view* in, const svs_patch_view* out,
+                            const int32_t* in_frames, int batch, int flags, void* workspace,
+                            size_t workspace_bytes, int first_layer, int last_layer, void* stream);
+
 /* Debug / parity hook: copy an intermediate activation of the LAST svs_unet_forward call on this
  * workspace out as fp32 NCHW.  layer 0..5 = conv1..conv6 outputs, 6..10 = deconv1..deconv5 outputs. */
 int svs_unet_read_activation(const svs_unet_plan* plan, int layer, int batch, const void* workspace,

@@ -62,6 +62,8 @@ _SIGNATURES = [
     ("svs_unet_workspace_bytes", c_size_t, [c_void_p, c_int]),
     ("svs_unet_forward", c_int, [c_void_p, POINTER(PatchView), POINTER(PatchView), c_void_p, c_int, c_int,
                                  c_void_p, c_size_t, c_void_p]),
+    ("svs_unet_forward_layers", c_int, [c_void_p, POINTER(PatchView), POINTER(PatchView), c_void_p, c_int, c_int,
+                                        c_void_p, c_size_t, c_int, c_int, c_void_p]),
     ("svs_unet_read_activation", c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     ("svs_unet_launch_count", c_int, [c_void_p, c_int]),
     ("svs_unet_train_workspace_bytes", c_size_t, [c_int]),
@@ -263,12 +265,14 @@ class UNetPlan:
     def launch_count(self, batch: int) -> int:
         return load().svs_unet_launch_count(self.handle, batch)
 
-    def forward_views(self, in_view: PatchView, out_view: PatchView, in_frames, batch: int, flags: int):
+    def forward_views(self, in_view: PatchView, out_view: PatchView, in_frames, batch: int, flags: int,
+                      first_layer: int = 0, last_layer: int = 11):
         ws = self.workspace(batch)
         with torch.cuda.device(self.device):
-            check(load().svs_unet_forward(self.handle, byref(in_view), byref(out_view),
-                                          in_frames.data_ptr() if in_frames is not None else None, batch, flags,
-                                          ws.data_ptr(), ws.numel(), stream_ptr(self.device)),
+            check(load().svs_unet_forward_layers(self.handle, byref(in_view), byref(out_view),
+                                                 in_frames.data_ptr() if in_frames is not None else None, batch,
+                                                 flags, ws.data_ptr(), ws.numel(), first_layer, last_layer,
+                                                 stream_ptr(self.device)),
                   "svs_unet_forward")
 
     def forward_dense(self, mix: torch.Tensor, flags: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:

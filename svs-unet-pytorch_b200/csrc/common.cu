@@ -17,9 +17,13 @@ int fail(int code, const std::string& msg) {
 }
 
 int num_sms() {
-  int dev = 0, n = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  return n;
+  static int cached = 0;     // one process drives one GPU model; all B200s report 148
+  if (cached == 0) {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached = n;
+  }
+  return cached;
 }
 
 namespace {

@@ -20,6 +20,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
 #include "unet_internal.cuh"
+#include "tc_ptx.cuh"
 
 #include <cudaTypedefs.h>
 #include <cstdlib>
@@ -28,121 +29,12 @@
 namespace svs {
 
 // ---------------------------------------------------------------------------------------------
-// PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
-                                            int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int kCols>
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(kCols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int kCols>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA
-template <bool kTf32>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                     uint32_t accumulate) {
-  if constexpr (kTf32) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-// arrives on the mbarrier once every previously issued MMA of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major operand descriptor for a [rows][kSwz bytes] tile in the kSwz-byte swizzled canonical layout
-// (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61.
-template <int kSwz>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  constexpr uint64_t layout = kSwz == 128 ? 2 : (kSwz == 64 ? 4 : 6);
-  constexpr uint64_t sbo = (8 * kSwz) >> 4;      // 8-row core-matrix group pitch
-  return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
-         (layout << 61);
-}
-// cute::UMMA::InstrDescriptor: c_format F32 @4, a/b format @7/@10, K-major both, N>>3 @17, M>>4 @24
-template <bool kTf32, int kN>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-  const uint32_t fmt = kTf32 ? 2u : 1u;          // TF32 : BF16
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kN >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-// ---------------------------------------------------------------------------------------------
 struct TcParams {
   const TcChunk* chunks;
   int n_chunks[4], chunk_begin[4], py[4], px[4];
   int n_phases, split_k;
   int ntw, nth;                  // M tiles along w and h of the pixel grid
+  int m_tiles, n_tiles;          // tile counts (M includes the batch dimension)
   int bw, bh, nb;
   int batch;
   int block_k;                   // K elements per chunk
@@ -152,7 +44,9 @@ struct TcParams {
   int act;
   float* partial;
   int m_pad;                     // rows per (phase, split) slab of `partial`
-  int cout;
+  int cout;                      // GEMM N (merged deconv: 4 x channels)
+  int merged;                    // 1: N = 4 phases x cout_phase channels
+  int cout_phase;
 };
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -184,6 +78,11 @@ constexpr size_t tc_smem_bytes() {
   return static_cast<size_t>(kStages) * (128 + kBlockN) * kSwz + 1024 /*alignment slack*/ + 256 /*barriers*/;
 }
 
+
+// Persistent kernel: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is
+// double buffered in TMEM so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
+// tile index -> (z = phase * split_k + split, n tile, m tile) with m fastest (neighbouring CTAs share
+// the same weight tile in L2).
 template <typename OutT, bool kTf32, int kBlockN, int kSwz, int kStages>
 __global__ void __launch_bounds__(kTcThreads)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b0,
@@ -192,7 +91,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int kABytes = 128 * kSwz;
   constexpr int kBBytes = kBlockN * kSwz;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kTmemCols = kBlockN < 32 ? 32 : kBlockN;
+  constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;  // columns per accumulator stage
+  constexpr int kTmemCols = 2 * kAccCols;
   constexpr int kMmaPerChunk = kSwz / 32;          // UMMA_K is 32 bytes for bf16 (16) and tf32 (8)
 
   extern __shared__ uint8_t smem_raw[];
@@ -201,33 +101,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t bar_base = smem_base + kStages * kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 1));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int phase = blockIdx.z / p.split_k;
-  const int split = blockIdx.z - phase * p.split_k;
-  const int n_chunks = p.n_chunks[phase];
-  const int per_split = (n_chunks + p.split_k - 1) / p.split_k;
-  const int c_begin = split * per_split;
-  const int c_end = min(n_chunks, c_begin + per_split);
-  const int n_iter = max(0, c_end - c_begin);
-
-  const int tw = blockIdx.x % p.ntw;
-  const int th = (blockIdx.x / p.ntw) % p.nth;
-  const int tb = blockIdx.x / (p.ntw * p.nth);
-  const int n0 = blockIdx.y * kBlockN;
+  const int m_tiles = p.m_tiles, n_tiles = p.n_tiles;
+  const int per_z = m_tiles * n_tiles;
+  const int total_tiles = per_z * p.n_phases * p.split_k;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
     fence_barrier_init();
     tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(phase == 0 ? &tmap_b0 : phase == 1 ? &tmap_b1 : phase == 2 ? &tmap_b2 : &tmap_b3);
+    tma_prefetch_desc(&tmap_b0);
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
@@ -238,41 +130,64 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const CUtensorMap* tb_map = phase == 0 ? &tmap_b0 : phase == 1 ? &tmap_b1 : phase == 2 ? &tmap_b2 : &tmap_b3;
-      const TcChunk* chunks = p.chunks + p.chunk_begin[phase];
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kStages;
-        const uint32_t par = (it / kStages) & 1;
-        mbar_wait(empty_bar(s), par ^ 1);
-        mbar_expect_tx(full_bar(s), kStageBytes);
-        const int ci = c_begin + it;
-        const TcChunk ch = chunks[ci];
-        const uint32_t a_dst = smem_base + s * kStageBytes;
-        tma_load_5d(a_dst, &tmap_a, full_bar(s), ch.c_inner, tw * p.bw + ch.dw, ch.ph, th * p.bh + ch.dh,
-                    tb * p.nb);
-        tma_load_2d(a_dst + kABytes, tb_map, full_bar(s), ci * p.block_k, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile / per_z, rem = tile - z * per_z;
+        const int nt = rem / m_tiles, mt = rem - nt * m_tiles;
+        const int phase = z / p.split_k, split = z - phase * p.split_k;
+        const int n_chunks = p.n_chunks[phase];
+        const int per_split = (n_chunks + p.split_k - 1) / p.split_k;
+        const int c_begin = split * per_split;
+        const int c_end = min(n_chunks, c_begin + per_split);
+        const int tw = mt % p.ntw, th = (mt / p.ntw) % p.nth, tb = mt / (p.ntw * p.nth);
+        const CUtensorMap* tb_map = phase == 0 ? &tmap_b0 : phase == 1 ? &tmap_b1 : phase == 2 ? &tmap_b2 : &tmap_b3;
+        const TcChunk* chunks = p.chunks + p.chunk_begin[phase];
+        for (int ci = c_begin; ci < c_end; ++ci, ++it) {
+          const int s = it % kStages;
+          const uint32_t par = (it / kStages) & 1;
+          mbar_wait(empty_bar(s), par ^ 1);
+          mbar_expect_tx(full_bar(s), kStageBytes);
+          const TcChunk ch = chunks[ci];
+          const uint32_t a_dst = smem_base + s * kStageBytes;
+          tma_load_5d(a_dst, &tmap_a, full_bar(s), ch.c_inner, tw * p.bw + ch.dw, ch.ph, th * p.bh + ch.dh,
+                      tb * p.nb);
+          tma_load_2d(a_dst + kABytes, tb_map, full_bar(s), ci * p.block_k, nt * kBlockN);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<kTf32, kBlockN>();
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % kStages;
-        const uint32_t par = (it / kStages) & 1;
-        mbar_wait(full_bar(s), par);
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int z = tile / per_z;
+        const int phase = z / p.split_k, split = z - phase * p.split_k;
+        const int n_chunks = p.n_chunks[phase];
+        const int per_split = (n_chunks + p.split_k - 1) / p.split_k;
+        const int c_begin = split * per_split;
+        const int n_iter = max(0, min(n_chunks, c_begin + per_split) - c_begin);
+        const int as = t & 1;
+        mbar_wait(tmem_empty_bar(as), ((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * kStageBytes;
-        const uint64_t da = make_smem_desc<kSwz>(a_addr);
-        const uint64_t db = make_smem_desc<kSwz>(a_addr + kABytes);
+        const uint32_t tmem_d = tmem_base + as * kAccCols;
+        for (int i = 0; i < n_iter; ++i, ++it) {
+          const int s = it % kStages;
+          const uint32_t par = (it / kStages) & 1;
+          mbar_wait(full_bar(s), par);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * kStageBytes;
+          const uint64_t da = make_smem_desc<kSwz>(a_addr);
+          const uint64_t db = make_smem_desc<kSwz>(a_addr + kABytes);
 #pragma unroll
-        for (int k = 0; k < kMmaPerChunk; ++k) {
-          // advance 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-          umma<kTf32>(tmem_base, da + 2u * k, db + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kMmaPerChunk; ++k) {
+            // advance 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma<kTf32>(tmem_d, da + 2u * k, db + 2u * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
+        umma_commit(tmem_full_bar(as));         // accumulator complete
       }
-      umma_commit(tmem_full_bar);             // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
@@ -281,53 +196,74 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int iw = r % p.bw;
     const int ih = (r / p.bw) % p.bh;
     const int ib = r / (p.bw * p.bh);
-    const int gx = tw * p.bw + iw, gy = th * p.bh + ih, b = tb * p.nb + ib;
-    const bool valid = b < p.batch;
-    if (n_iter > 0) {
-      mbar_wait(tmem_full_bar, 0);
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int z = tile / per_z, rem = tile - z * per_z;
+      const int nt = rem / m_tiles, mt = rem - nt * m_tiles;
+      const int phase = z / p.split_k, split = z - phase * p.split_k;
+      const int n_chunks = p.n_chunks[phase];
+      const int per_split = (n_chunks + p.split_k - 1) / p.split_k;
+      const int c_begin = split * per_split;
+      const int n_iter = max(0, min(n_chunks, c_begin + per_split) - c_begin);
+      const int tw = mt % p.ntw, th = (mt / p.ntw) % p.nth, tb = mt / (p.ntw * p.nth);
+      const int n0 = nt * kBlockN;
+      const int gx = tw * p.bw + iw, gy = th * p.bh + ih, b = tb * p.nb + ib;
+      const bool valid = b < p.batch;
+      const int as = t & 1;
+      mbar_wait(tmem_full_bar(as), (t >> 1) & 1);
       tc_fence_after();
-    }
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
-    if (p.split_k == 1) {
-      const int oy = gy * p.out_scale + p.py[phase], ox = gx * p.out_scale + p.px[phase];
-      OutT* dst = reinterpret_cast<OutT*>(p.out) +
-                  ((static_cast<size_t>(b) * p.hout + oy) * p.wout + ox) * p.out_pitch + p.out_coff + n0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccCols;
+      if (p.split_k == 1) {
+        OutT* const out_base = reinterpret_cast<OutT*>(p.out);
 #pragma unroll 1
-      for (int c = 0; c < kBlockN; c += 16) {
-        uint32_t v[16];
-        float f[16];
-        if (n_iter > 0) {
-          tmem_ld16(taddr + c, v);
-          tmem_ld_wait();
-        } else {
+        for (int c = 0; c < kBlockN; c += 16) {
+          uint32_t v[16];
+          float f[16];
+          if (n_iter > 0) {
+            tmem_ld16(taddr + c, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+          }
+          // merged deconv: 16-column groups never straddle a phase (channels per phase >= 16)
+          int py = p.py[phase], px = p.px[phase], ch = n0 + c;
+          if (p.merged) {
+            const int ph = ch / p.cout_phase;
+            ch -= ph * p.cout_phase;
+            py = ph >> 1; px = ph & 1;
+          }
+          const int oy = gy * p.out_scale + py, ox = gx * p.out_scale + px;
+          OutT* dst = out_base + ((static_cast<size_t>(b) * p.hout + oy) * p.wout + ox) * p.out_pitch + p.out_coff + ch;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = tc_act(__uint_as_float(v[i]) + __ldg(&p.bias[ch + i]), p.act);
+          if (valid) store16(dst, f);
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = tc_act(__uint_as_float(v[i]) + __ldg(&p.bias[n0 + c + i]), p.act);
-        if (valid) store16(dst + c, f);
-      }
-    } else {
-      float* dst = p.partial +
-                   (static_cast<size_t>(blockIdx.z) * p.m_pad + static_cast<size_t>(blockIdx.x) * 128 + r) * p.cout + n0;
+      } else {
+        float* dst = p.partial +
+                     (static_cast<size_t>(z) * p.m_pad + static_cast<size_t>(mt) * 128 + r) * p.cout + n0;
 #pragma unroll 1
-      for (int c = 0; c < kBlockN; c += 16) {
-        uint32_t v[16];
-        float f[16];
-        if (n_iter > 0) {
-          tmem_ld16(taddr + c, v);
-          tmem_ld_wait();
-        } else {
+        for (int c = 0; c < kBlockN; c += 16) {
+          uint32_t v[16];
+          float f[16];
+          if (n_iter > 0) {
+            tmem_ld16(taddr + c, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          store16(dst + c, f);
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        store16(dst + c, f);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(as));      // 4 warps -> accumulator stage is free
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -393,6 +329,31 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w_fold, int cin
   }
 }
 
+// merged deconv: B[n = phase*cout + co][k = chunk*bk + kk]; chunk_src = ((dh+1)*3 + (dw+1), ci0);
+// phase (py, px) uses tap (kh, kw) = (py + 2 - 2 dh, px + 2 - 2 dw) when it lies in [0, 4], else zero.
+template <typename E>
+__global__ void tc_pack_weights_merged_kernel(const float* __restrict__ w_fold, int cin, int cout,
+                                              const int2* __restrict__ chunk_src, int n_chunks, int bk,
+                                              E* __restrict__ out) {
+  const int k_total = n_chunks * bk;
+  const size_t total = static_cast<size_t>(4 * cout) * k_total;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / k_total);
+    const int k = static_cast<int>(i % k_total);
+    const int ph = n / cout, co = n % cout;
+    const int py = ph >> 1, px = ph & 1;
+    const int2 src = chunk_src[k / bk];
+    const int dh = src.x / 3 - 1, dw = src.x % 3 - 1;
+    const int kh = py + 2 - 2 * dh, kw = px + 2 - 2 * dw;
+    float v = 0.0f;
+    if (kh >= 0 && kh <= 4 && kw >= 0 && kw <= 4)
+      v = w_fold[(static_cast<size_t>(kh * 5 + kw) * cin + src.y + (k % bk)) * cout + co];
+    if constexpr (sizeof(E) == 2) out[i] = __float2bfloat16_rn(v);
+    else out[i] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 static PFN_cuTensorMapEncodeTiled get_encode_fn() {
@@ -408,7 +369,7 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* map, bool tf32, int rank, void* base, const cuuint64_t* dims,
+int encode_tensor_map(CUtensorMap* map, bool tf32, int rank, void* base, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box, int swz) {
   PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
   if (!fn) return fail(SVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -436,7 +397,7 @@ static int make_tmap_a(const TcLayer& t, const LayerGeom& g, void* buf, int batc
   }
   const cuuint32_t box[5] = {static_cast<cuuint32_t>(t.block_k), static_cast<cuuint32_t>(t.bw), 1,
                              static_cast<cuuint32_t>(t.bh), static_cast<cuuint32_t>(t.nb)};
-  return encode_map(out, tf32, 5, buf, dims, strides, box, t.swz);
+  return encode_tensor_map(out, tf32, 5, buf, dims, strides, box, t.swz);
 }
 
 static unsigned tc_disable_mask() {
@@ -456,7 +417,10 @@ int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
     if (swz < 32 || (disable >> li) & 1u) continue;     // conv2 in bf16 would be 32-byte rows: allowed
     t.swz = swz;
     t.block_k = swz / es;
-    t.block_n = g.cout < 128 ? g.cout : 128;
+    const char* no_merge = std::getenv("SVS_TC_NO_MERGE");
+    t.merged = g.transposed && 4 * g.cout <= 256 && !(no_merge && no_merge[0] == '1');
+    const int n_total = t.merged ? 4 * g.cout : g.cout;
+    t.block_n = n_total < 256 ? (n_total < 128 ? n_total : 128) : (t.merged ? 256 : 128);
     t.gw = g.transposed ? g.win : g.wout;
     t.gh = g.transposed ? g.hin : g.hout;
     t.bw = t.gw < 16 ? t.gw : 16;
@@ -479,6 +443,16 @@ int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
             src.push_back(make_int2(kh * 5 + kw, c0));
           }
         }
+      t.phases[0].n_chunks = static_cast<int>(t.chunks.size());
+    } else if (t.merged) {
+      t.n_phases = 1;
+      t.phases[0] = TcPhase{0, 0, 0, 0, 0};
+      for (int dh = 1; dh >= -1; --dh)
+        for (int dw = 1; dw >= -1; --dw)
+          for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
+            t.chunks.push_back(TcChunk{g.in_coff + c0, dw, 0, dh});
+            src.push_back(make_int2((dh + 1) * 3 + (dw + 1), c0));
+          }
       t.phases[0].n_chunks = static_cast<int>(t.chunks.size());
     } else {
       t.n_phases = 4;
@@ -506,16 +480,24 @@ int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
     SVS_CUDA_TRY(cudaMemcpyAsync(t.d_chunks, t.chunks.data(), sizeof(TcChunk) * n_chunks_total,
                                  cudaMemcpyHostToDevice, st));
     SVS_CUDA_TRY(cudaMemcpyAsync(d_src, src.data(), sizeof(int2) * n_chunks_total, cudaMemcpyHostToDevice, st));
-    const size_t w_elems = n_chunks_total * t.block_k * g.cout;
+    const size_t w_elems = n_chunks_total * t.block_k * n_total;
     SVS_CUDA_TRY(cudaMalloc(&t.d_weights, w_elems * es));
     size_t off = 0;
     for (int ph = 0; ph < t.n_phases; ++ph) {
       TcPhase& phs = t.phases[ph];
       phs.b_elem_off = static_cast<int64_t>(off);
       t.k_total[ph] = phs.n_chunks * t.block_k;
-      const size_t n = static_cast<size_t>(g.cout) * t.k_total[ph];
+      const size_t n = static_cast<size_t>(n_total) * t.k_total[ph];
       const unsigned blocks = static_cast<unsigned>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
-      if (tf32)
+      if (t.merged && tf32)
+        tc_pack_weights_merged_kernel<float><<<blocks, 256, 0, st>>>(plan->w_fold[li], g.cin, g.cout, d_src,
+                                                                    phs.n_chunks, t.block_k,
+                                                                    static_cast<float*>(t.d_weights));
+      else if (t.merged)
+        tc_pack_weights_merged_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+            plan->w_fold[li], g.cin, g.cout, d_src, phs.n_chunks, t.block_k,
+            static_cast<__nv_bfloat16*>(t.d_weights));
+      else if (tf32)
         tc_pack_weights_kernel<float><<<blocks, 256, 0, st>>>(plan->w_fold[li], g.cin, g.cout,
                                                              d_src + phs.chunk_begin, phs.n_chunks, t.block_k,
                                                              static_cast<float*>(t.d_weights) + off);
@@ -525,10 +507,10 @@ int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
             static_cast<__nv_bfloat16*>(t.d_weights) + off);
       SVS_CHECK_LAUNCH("tc_pack_weights_kernel");
       // B tensor map: [Cout][K] K-major
-      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(t.k_total[ph]), static_cast<cuuint64_t>(g.cout)};
+      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(t.k_total[ph]), static_cast<cuuint64_t>(n_total)};
       const cuuint64_t strides[1] = {static_cast<cuuint64_t>(t.k_total[ph]) * es};
       const cuuint32_t box[2] = {static_cast<cuuint32_t>(t.block_k), static_cast<cuuint32_t>(t.block_n)};
-      int rc = encode_map(&t.tmap_b[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides, box,
+      int rc = encode_tensor_map(&t.tmap_b[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides, box,
                           t.swz);
       if (rc != SVS_OK) return rc;
       off += n;
@@ -553,7 +535,7 @@ void tc_free_layers(svs_unet_plan* plan) {
 void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, int* split_k) {
   const int ntw = t.gw / t.bw, nth = t.gh / t.bh, ntb = (batch + t.nb - 1) / t.nb;
   *m_tiles = ntw * nth * ntb;
-  const int n_tiles = g.cout / t.block_n;
+  const int n_tiles = (t.merged ? 4 * g.cout : g.cout) / t.block_n;
   const int tiles = *m_tiles * n_tiles * t.n_phases;
   int min_chunks = 1 << 30;
   for (int ph = 0; ph < t.n_phases; ++ph) min_chunks = t.phases[ph].n_chunks < min_chunks ? t.phases[ph].n_chunks : min_chunks;
@@ -563,7 +545,7 @@ void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, in
   else if (tiles < 120) s = 148 / tiles;
   if (s > 8) s = 8;
   if (s > min_chunks / 4) s = min_chunks / 4;
-  if (s < 1) s = 1;
+  if (s < 1 || t.merged) s = 1;
   *split_k = s;
 }
 
@@ -589,10 +571,18 @@ int tc_launch_count(const svs_unet_plan* plan, int li, int batch) {
 }
 
 template <typename OutT, bool kTf32, int kBlockN, int kSwz, int kStages>
-static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p, dim3 grid, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p, int total_tiles, cudaStream_t st) {
   auto kern = tc_conv_kernel<OutT, kTf32, kBlockN, kSwz, kStages>;
   constexpr size_t smem = tc_smem_bytes<kBlockN, kSwz, kStages>();
   SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // resident CTAs per SM: shared memory, TMEM columns (2 accumulator stages) and a cap of 3
+  constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  if (per_sm > 512 / (2 * kAccCols)) per_sm = 512 / (2 * kAccCols);
+  if (per_sm > 3) per_sm = 3;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > total_tiles) grid = total_tiles;
   kern<<<grid, kTcThreads, smem, st>>>(ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2], t.tmap_b[3], p);
   SVS_CHECK_LAUNCH("tc_conv_kernel");
   return SVS_OK;
@@ -640,16 +630,21 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   p.act = g.act;
   p.partial = ws.splitk;
   p.m_pad = m_tiles * 128;
-  p.cout = g.cout;
+  p.cout = t.merged ? 4 * g.cout : g.cout;
+  p.merged = t.merged ? 1 : 0;
+  p.cout_phase = g.cout;
   if (split > 1 && ws.splitk_bytes < static_cast<size_t>(split) * t.n_phases * p.m_pad * g.cout * sizeof(float))
     return fail(SVS_ERR_WORKSPACE, "tc_launch_layer: split-K scratch too small");
-  dim3 grid(m_tiles, g.cout / t.block_n, t.n_phases * split);
+  p.m_tiles = m_tiles;
+  p.n_tiles = p.cout / t.block_n;
+  const int grid = m_tiles * p.n_tiles * t.n_phases * split;
   int rc = SVS_ERR_NOT_IMPLEMENTED;
 #define SVS_TC_CASE(N, S, ST)                                                                       \
   if (t.block_n == N && t.swz == S) {                                                               \
     rc = tf32 ? launch_tc<float, true, N, S, ST>(ta, t, p, grid, st)                                \
               : launch_tc<__nv_bfloat16, false, N, S, ST>(ta, t, p, grid, st);                      \
   }
+  SVS_TC_CASE(256, 128, 3)
   SVS_TC_CASE(128, 128, 3)
   SVS_TC_CASE(64, 128, 4)
   SVS_TC_CASE(32, 128, 4)

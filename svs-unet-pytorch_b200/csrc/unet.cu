@@ -6,6 +6,7 @@
 // state, so it can be captured into a CUDA graph.
 #include "unet_internal.cuh"
 
+#include <cstdlib>
 #include <new>
 
 namespace svs {
@@ -23,6 +24,11 @@ void tc_free_layers(svs_unet_plan* plan);
 size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch);
 int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st);
 int tc_launch_count(const svs_unet_plan* plan, int li, int batch);
+// deconv6_tc.cu
+int d6_plan(svs_unet_plan* plan, cudaStream_t st);
+void d6_free(svs_unet_plan* plan);
+int d6_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_view* in, const svs_patch_view* out,
+              const int32_t* in_frames, int batch, int flags, cudaStream_t st);
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -83,6 +89,11 @@ extern "C" int svs_unet_plan_create(const svs_conv_params layers[12], int precis
   if (precision != SVS_PRECISION_FP32) {
     rc = tc_plan_layers(plan, st);
     if (rc != SVS_OK) { svs_unet_plan_destroy(plan); return rc; }
+    const char* dis = std::getenv("SVS_TC_DISABLE_MASK");
+    if (!(dis && ((std::strtoul(dis, nullptr, 0) >> 11) & 1u))) {
+      rc = d6_plan(plan, st);
+      if (rc != SVS_OK) { svs_unet_plan_destroy(plan); return rc; }
+    }
   }
   *plan_out = plan;
   return SVS_OK;
@@ -91,6 +102,7 @@ extern "C" int svs_unet_plan_create(const svs_conv_params layers[12], int precis
 extern "C" int svs_unet_plan_destroy(svs_unet_plan* plan) {
   if (!plan) return SVS_OK;
   tc_free_layers(plan);
+  d6_free(plan);
   for (int i = 0; i < 12; ++i) {
     if (plan->w_fold[i]) cudaFree(plan->w_fold[i]);
     if (plan->b_fold[i]) cudaFree(plan->b_fold[i]);
@@ -111,7 +123,15 @@ extern "C" size_t svs_unet_workspace_bytes(const svs_unet_plan* plan, int batch)
 extern "C" int svs_unet_forward(const svs_unet_plan* plan, const svs_patch_view* in, const svs_patch_view* out,
                                 const int32_t* in_frames, int batch, int flags, void* workspace,
                                 size_t workspace_bytes, void* stream) {
+  return svs_unet_forward_layers(plan, in, out, in_frames, batch, flags, workspace, workspace_bytes, 0, 11, stream);
+}
+
+extern "C" int svs_unet_forward_layers(const svs_unet_plan* plan, const svs_patch_view* in,
+                                       const svs_patch_view* out, const int32_t* in_frames, int batch, int flags,
+                                       void* workspace, size_t workspace_bytes, int first_layer, int last_layer,
+                                       void* stream) {
   SVS_REQUIRE(plan && in && out && in->base && out->base && workspace, "svs_unet_forward: null pointer");
+  SVS_REQUIRE(first_layer >= 0 && last_layer <= 11 && first_layer <= last_layer, "svs_unet_forward_layers: bad layer range");
   SVS_REQUIRE(batch > 0, "svs_unet_forward: batch must be positive");
   SVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
               "svs_unet_forward: workspace must be 1024-byte aligned");
@@ -121,9 +141,10 @@ extern "C" int svs_unet_forward(const svs_unet_plan* plan, const svs_patch_view*
     return fail(SVS_ERR_WORKSPACE, "svs_unet_forward: workspace too small (need " +
                                        std::to_string(ws.total_bytes) + " bytes)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (int li = 0; li < 12; ++li) {
+  for (int li = first_layer; li <= last_layer; ++li) {
     int rc;
-    if (plan->tc[li].enabled) rc = tc_launch_layer(plan, li, ws, batch, st);
+    if (li == 11 && plan->d6_enabled) rc = d6_launch(plan, ws, in, out, in_frames, batch, flags, st);
+    else if (plan->tc[li].enabled) rc = tc_launch_layer(plan, li, ws, batch, st);
     else rc = launch_layer_direct(plan, li, ws, in, out, in_frames, batch, flags, st);
     if (rc != SVS_OK) return rc;
   }

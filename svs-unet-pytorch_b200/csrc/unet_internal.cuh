@@ -79,6 +79,8 @@ struct TcLayer {
   int swz = 128;                     // bytes of K per smem row == TMA/UMMA swizzle span (32/64/128)
   int block_k = 0;                   // K elements per chunk = swz / elem_size
   int n_phases = 1;
+  bool merged = false;               // deconv: all 4 sub-pixel phases stacked along N (zero weights where a
+                                     // phase does not use a tap) so each input slab is loaded once, not 25/9 times
   TcPhase phases[4];
   std::vector<TcChunk> chunks;       // host copy
   TcChunk* d_chunks = nullptr;       // device copy
@@ -100,4 +102,8 @@ struct svs_unet_plan {
   float* w_fold[12] = {};            // folded fp32 weights [25][Cin][Cout]
   float* b_fold[12] = {};            // folded fp32 bias [Cout]
   svs::TcLayer tc[12];
+  // deconv6 as a taps-as-N GEMM + col2im gather (deconv6_tc.cu)
+  bool d6_enabled = false;
+  void* d6_weights = nullptr;
+  CUtensorMap d6_tmap_w;
 };
