@@ -1,0 +1,128 @@
+"""Device-resident separation pipeline:  audio -> STFT -> /max -> UNet mask x mixture -> iSTFT -> 0.9 peak.
+
+This is the three reference CLI stages (data.py to_spec -> inference.py -> data.py to_wave, joined by
+.npy files on disk in the reference: inference.py:135-150) as ONE pass that keeps every spectrogram in
+HBM.  The patch logic restates reference inference.py:65-127:
+
+* the DC row is dropped on the way in (a +1 element offset) and re-inserted as zeros on the way out,
+* the time axis is cut into 128-frame patches, ``T // 128 + 1`` of them with the empty one skipped,
+* the last patch is zero padded (frames >= valid are read as 0 by conv1) and cropped (not written).
+
+Nothing is copied to build patches: the UNet kernels read / write the frame-major spectrogram
+([T][513], i.e. librosa's Fortran-ordered (513, T)) through a strided patch view.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import INPUT_LEN, N_BINS
+from .spectral import SongBatch
+
+
+def patch_table(frames_per_song, frame_off):
+    """Host-side patch table (reference inference.py:75-92).  Returns (elem_off int64[P], valid int32[P],
+    song int32[P]) where elem_off indexes a [total_frames][513] float32 spectrogram (DC bin skipped)."""
+    offs, valid, song = [], [], []
+    for s, t in enumerate(frames_per_song):
+        for i in range(t // INPUT_LEN + 1):
+            cur = min(INPUT_LEN, t - i * INPUT_LEN)
+            if cur <= 0:
+                continue                                              # inference.py:88
+            offs.append((int(frame_off[s]) + i * INPUT_LEN) * N_BINS + 1)
+            valid.append(cur)
+            song.append(s)
+    return (np.asarray(offs, dtype=np.int64), np.asarray(valid, dtype=np.int32), np.asarray(song, dtype=np.int32))
+
+
+class Separator:
+    """Runs whole songs through the fused path on one GPU."""
+
+    def __init__(self, model, max_batch: int = 64):
+        self.model = model
+        self.max_batch = int(max_batch)
+
+    @torch.no_grad()
+    def separate_batch(self, batch: SongBatch, vocal_solo: bool = True, peak_normalize: bool = True,
+                       return_spec: bool = False):
+        """SongBatch (device audio) -> (wave [total_wave] f32 device, peak [n_songs]); optionally also the
+        normalised mixture spectrogram, the phase and the masked spectrogram ([F,513] layouts)."""
+        plan = self.model.plan()
+        mag, phase, smax = batch.stft()
+        batch.normalize(mag, smax)                                    # data.py:105
+        offs, valid, _ = patch_table(batch.frames, batch.frame_off_host)
+        dev = mag.device
+        d_off = torch.from_numpy(offs).to(dev)
+        d_valid = torch.from_numpy(valid).to(dev)
+        out_mag = torch.zeros_like(mag)                               # DC row stays 0 (inference.py:123)
+        flags = _lib.FLAG_APPLY_MASK | (0 if vocal_solo else _lib.FLAG_INVERT)
+        n = len(offs)
+        for a in range(0, n, self.max_batch):
+            b = min(n, a + self.max_batch)
+            iv = _lib.PatchView(mag.data_ptr(), d_off[a:b].data_ptr(), 0, 1, N_BINS)
+            ov = _lib.PatchView(out_mag.data_ptr(), d_off[a:b].data_ptr(), 0, 1, N_BINS)
+            plan.forward_views(iv, ov, d_valid[a:b], b - a, flags)
+        wave, peak = batch.istft(out_mag, phase, peak_normalize=peak_normalize)   # data.py:159-164
+        if return_spec:
+            return wave, peak, mag, phase, out_mag
+        return wave, peak
+
+    def separate(self, songs, vocal_solo: bool = True, peak_normalize: bool = True):
+        """list of 1-D float32 host arrays -> list of float32 numpy waveforms (len 768 * (T - 1))."""
+        batch = SongBatch.from_audio(songs, device=next(self.model.parameters()).device)
+        wave, _ = self.separate_batch(batch, vocal_solo, peak_normalize)
+        host = wave.cpu().numpy()
+        return [host[int(batch.wave_off_host[s]): int(batch.wave_off_host[s]) + batch.wave_lengths[s]]
+                for s in range(batch.n_songs)]
+
+
+class PatchStreamer:
+    """Host-buffer entry point for patch batches: pinned host -> device -> UNet -> pinned host, with the
+    H2D copy of batch i+1 and the D2H copy of batch i-1 overlapping the kernels of batch i (three
+    streams, double-buffered device staging).  Mirrors what reference inference.py:97-110 does one
+    patch at a time with a synchronous .to(device) / .cpu() pair."""
+
+    def __init__(self, model, batch: int = 64, vocal_solo: bool | None = None):
+        self.model = model
+        self.batch = batch
+        self.flags = 0 if vocal_solo is None else (_lib.FLAG_APPLY_MASK | (0 if vocal_solo else _lib.FLAG_INVERT))
+        dev = next(model.parameters()).device
+        self.dev = dev
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        shape = (batch, 1, 512, 128)
+        self.d_in = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.d_out = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.plan = model.plan()
+
+    @torch.no_grad()
+    def run(self, host_in, host_out):
+        """host_in / host_out: sequences of pinned float32 tensors (batch,1,512,128).  Returns after the
+        last result has landed in host memory."""
+        n = len(host_in)
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_stream(cur)
+        for i in range(n):
+            k = i & 1
+            with torch.cuda.stream(self.s_in):
+                if i >= 2:
+                    self.s_in.wait_event(self.ev_cmp[k])              # staging buffer k was consumed
+                self.d_in[k].copy_(host_in[i], non_blocking=True)
+                self.ev_in[k].record(self.s_in)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(self.ev_in[k])
+                if i >= 2:
+                    self.s_cmp.wait_event(self.ev_out[k])             # result buffer k was drained
+                self.plan.forward_dense(self.d_in[k], self.flags, self.d_out[k])
+                self.ev_cmp[k].record(self.s_cmp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_cmp[k])
+                host_out[i].copy_(self.d_out[k], non_blocking=True)
+                self.ev_out[k].record(self.s_out)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_cmp)
+        cur.wait_stream(self.s_in)
