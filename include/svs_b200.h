@@ -158,6 +158,10 @@ int svs_unet_forward_layers(const svs_unet_plan* plan, const svs_patch_view* in,
                             const int32_t* in_frames, int batch, int flags, void* workspace,
                             size_t workspace_bytes, int first_layer, int last_layer, void* stream);
 
+/* Profiling hook: when non-NULL, every tcgen05 conv CTA of layer `layer` writes 8 clock64() stamps (start, setup done,
+ * first operands landed, MMAs issued, accumulator ready, epilogue done, exit) to device_buffer[8*cta]. */
+int svs_debug_set_trace(long long* device_buffer, int layer);
+
 /* Debug / parity hook: copy an intermediate activation of the LAST svs_unet_forward call on this
  * workspace out as fp32 NCHW.  layer 0..5 = conv1..conv6 outputs, 6..10 = deconv1..deconv5 outputs. */
 int svs_unet_read_activation(const svs_unet_plan* plan, int layer, int batch, const void* workspace,
@@ -167,26 +171,41 @@ int svs_unet_read_activation(const svs_unet_plan* plan, int layer, int batch, co
 int svs_unet_launch_count(const svs_unet_plan* plan, int batch);
 
 /* ------------------------------------------------------------------ training step (T1)
- * Forward in train mode (batch-statistic BatchNorm with running-stat update, Dropout2d via explicit
- * keep masks), masked-L1 loss of reference train.py:274-283 with crit = L1, and the backward pass.
- * Parameters and gradients are the raw fp32 torch tensors of the state_dict (no plan).
+ * Replaces the autograd graph of reference train.py:274-299 (mask = model(mix) in train mode, L1 loss,
+ * loss.backward()): train-mode forward (batch-statistic BatchNorm + running-stat update with momentum
+ * 0.1 / unbiased variance, Dropout2d through explicit per-(sample, channel) keep masks), the masked-L1
+ * loss of train.py:275-283 with crit = L1 (reference config.py:33,44), and the backward pass producing
+ * every parameter gradient.  Parameters and gradients are the raw fp32 torch tensors of the state_dict
+ * (torch layouts, no plan); torch.optim.Adam (reference model.py:116) consumes the gradients unchanged.
+ * Arithmetic is fp32; all reductions have a fixed order (bit-reproducible, no atomics).
  */
 typedef struct svs_train_layer {
-  float* weight;  float* bias;                 /* parameters (read)                                 */
-  float* bn_weight; float* bn_bias;            /* NULL for deconv6                                   */
-  float* bn_running_mean; float* bn_running_var;   /* updated in place (momentum 0.1, unbiased var) */
-  float* grad_weight; float* grad_bias;        /* written (overwritten, not accumulated)            */
+  const float* weight;  const float* bias;     /* parameters (read)                                    */
+  const float* bn_weight; const float* bn_bias;   /* NULL for deconv6                                  */
+  float* bn_running_mean; float* bn_running_var;  /* updated in place by the forward when requested    */
+  float* grad_weight; float* grad_bias;        /* written by the backward (overwritten, not accumulated) */
   float* grad_bn_weight; float* grad_bn_bias;
-  const uint8_t* dropout_keep;                 /* device [batch][Cout] 0/1 or NULL (= keep all)     */
+  const uint8_t* dropout_keep;                 /* device [batch][Cout] 0/1, or NULL (= keep all); only
+                                                  deconv1..deconv5 (reference model.py:80-108)            */
 } svs_train_layer;
 
 size_t svs_unet_train_workspace_bytes(int batch);
 
-/* loss_out: device float32 [3] = {total, vocal term, accompaniment term}; two_term: 1 = train.py
- * form, 0 = vocal term only.  update_running_stats: 1 in training. */
-int svs_unet_train_step(const svs_train_layer layers[12], const float* mix, const float* voc,
-                        int batch, int two_term, int update_running_stats, float* loss_out,
-                        void* workspace, size_t workspace_bytes, void* stream);
+/* mix float32 dense (batch,1,512,128) -> mask float32 dense (batch,1,512,128).  The workspace keeps
+ * everything the backward needs and must stay untouched until svs_unet_train_backward returns. */
+int svs_unet_train_forward(const svs_train_layer layers[12], const float* mix, int batch,
+                           int update_running_stats, float* mask_out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* grad_mask = dLoss/dmask (dense, same shape as the mask).  Fills grad_* of all 12 layers. */
+int svs_unet_train_backward(const svs_train_layer layers[12], const float* mix, const float* grad_mask,
+                            int batch, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused loss of reference train.py:275-283 and its gradient w.r.t. the mask:
+ *   L = mean|m*x - v| (+ mean|(1-m)*x - max(x - v, 0)| when two_term)      n = number of elements
+ * loss_out: device float32 [3] = {total, vocal term, accompaniment term}; grad_mask_out may be NULL. */
+int svs_l1_masked_loss(const float* mask, const float* mix, const float* voc, int64_t n, int two_term,
+                       float grad_scale, float* loss_out, float* grad_mask_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,11 +64,16 @@ _SIGNATURES = [
                                  c_void_p, c_size_t, c_void_p]),
     ("svs_unet_forward_layers", c_int, [c_void_p, POINTER(PatchView), POINTER(PatchView), c_void_p, c_int, c_int,
                                         c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    ("svs_debug_set_trace", c_int, [c_void_p, c_int]),
     ("svs_unet_read_activation", c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     ("svs_unet_launch_count", c_int, [c_void_p, c_int]),
     ("svs_unet_train_workspace_bytes", c_size_t, [c_int]),
-    ("svs_unet_train_step", c_int, [POINTER(TrainLayer), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                    c_void_p, c_size_t, c_void_p]),
+    ("svs_unet_train_forward", c_int, [POINTER(TrainLayer), c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]),
+    ("svs_unet_train_backward", c_int, [POINTER(TrainLayer), c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                        c_void_p]),
+    ("svs_l1_masked_loss", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p,
+                                   c_void_p]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 

@@ -53,6 +53,22 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = r;
 }
 
+__device__ __forceinline__ void store16v(float* p, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void store16v(__nv_bfloat16* p, const float (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // BatchNorm fold + repack.  conv: w[co][ci][kh][kw], deconv: w[ci][co][kh][kw]  ->  [tap][ci][co]
 // w' = w * gamma/sqrt(var+eps) along Cout, b' = (b - mean) * gamma/sqrt(var+eps) + beta.
@@ -92,50 +108,104 @@ int launch_fold_pack(const svs_conv_params& p, int cin, int cout, bool transpose
 }
 
 // ---------------------------------------------------------------------------------------------
-// U1.  One thread = one output pixel x 16 channels.  CTA tile 16x16 output pixels; the thread
-// index runs fastest along whichever input dimension is contiguous.
+// U1.  CTA = 8 output rows x all 64 output columns of one patch; the 19 x 128 input window is staged
+// once in shared memory (zero filled for the conv padding and for frames >= the patch's valid count),
+// each thread then computes 1 row x 4 columns x 16 channels from registers (1600 FMA per 20 vector
+// shared loads of input + 100 broadcast loads of weights).
+constexpr int kC1Rows = 8;                       // output rows per CTA
+constexpr int kC1Threads = 16 * kC1Rows;         // one thread = 1 row x 4 columns x 16 channels
+constexpr int kC1InRows = 2 * kC1Rows + 3;       // 35 input rows
+constexpr int kC1Pitch = 136;                    // 4 left pad + 128 + 4 right pad floats
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kC1Threads)
 conv1_kernel(const float* __restrict__ in, const int64_t* __restrict__ patch_off, int64_t stride_b,
              int64_t stride_f, int64_t stride_t, const int32_t* __restrict__ in_frames,
              const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-             int out_pitch, int out_coff) {
-  __shared__ float sw[25 * 16];
-  __shared__ float sb[16];
-  for (int i = threadIdx.x; i < 400; i += 256) sw[i] = w[i];
+             int out_pitch, int out_coff, int act) {
+  __shared__ __align__(16) float sw[25 * 16];
+  __shared__ __align__(16) float sb[16];
+  __shared__ __align__(16) float tile[kC1InRows * kC1Pitch];
+  for (int i = threadIdx.x; i < 400; i += kC1Threads) sw[i] = w[i];
   if (threadIdx.x < 16) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int b = blockIdx.z;
-  const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
-  int oh, ow;
-  if (stride_t == 1) { ow = blockIdx.x * 16 + lx; oh = blockIdx.y * 16 + ly; }
-  else               { oh = blockIdx.y * 16 + lx; ow = blockIdx.x * 16 + ly; }
+  const int b = blockIdx.y;
+  const int oh0 = blockIdx.x * kC1Rows;
   const float* __restrict__ src = in + (patch_off ? patch_off[b] : b * stride_b);
   const int nf = in_frames ? in_frames[b] : SVS_PATCH_FRAMES;
-  float acc[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = sb[c];
-#pragma unroll
-  for (int kh = 0; kh < 5; ++kh) {
-    const int f = 2 * oh + kh - 2;
-    if (f < 0 || f >= SVS_PATCH_BINS) continue;
-#pragma unroll
-    for (int kw = 0; kw < 5; ++kw) {
-      const int t = 2 * ow + kw - 2;
-      if (t < 0 || t >= nf) continue;
-      const float x = __ldg(src + f * stride_f + t * stride_t);
-      const float* wt = sw + (kh * 5 + kw) * 16;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) acc[c] = fmaf(x, wt[c], acc[c]);
+  const int f0 = 2 * oh0 - 2;
+  // tile[r][c] = x[f0 + r][c - 4]
+  const bool vec_ok = stride_t == 1 && (stride_f & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (vec_ok) {                                  // dense patches: 16-byte loads, all in flight at once
+    for (int i = threadIdx.x; i < kC1InRows * (kC1Pitch / 4); i += kC1Threads) {
+      const int r = i / (kC1Pitch / 4), q = i - r * (kC1Pitch / 4);
+      const int f = f0 + r, t = 4 * (q - 1);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f >= 0 && f < SVS_PATCH_BINS && t >= 0 && t < SVS_PATCH_FRAMES) {
+        v = __ldg(reinterpret_cast<const float4*>(src + f * stride_f + t));
+        if (t + 0 >= nf) v.x = 0.f;
+        if (t + 1 >= nf) v.y = 0.f;
+        if (t + 2 >= nf) v.z = 0.f;
+        if (t + 3 >= nf) v.w = 0.f;
+      }
+      *reinterpret_cast<float4*>(&tile[r * kC1Pitch + 4 * q]) = v;
+    }
+  } else if (stride_t == 1) {
+    for (int i = threadIdx.x; i < kC1InRows * kC1Pitch; i += kC1Threads) {
+      const int r = i / kC1Pitch, c = i - r * kC1Pitch;
+      const int f = f0 + r, t = c - 4;
+      tile[i] = (f >= 0 && f < SVS_PATCH_BINS && t >= 0 && t < nf) ? __ldg(src + f * stride_f + t) : 0.0f;
+    }
+  } else {                                       // frequency-contiguous views: walk r fastest
+    for (int i = threadIdx.x; i < kC1InRows * kC1Pitch; i += kC1Threads) {
+      const int c = i / kC1InRows, r = i - c * kC1InRows;
+      const int f = f0 + r, t = c - 4;
+      tile[r * kC1Pitch + c] =
+          (f >= 0 && f < SVS_PATCH_BINS && t >= 0 && t < nf) ? __ldg(src + f * stride_f + t * stride_t) : 0.0f;
     }
   }
-  T* dst = out + ((static_cast<size_t>(b) * 256 + oh) * 64 + ow) * out_pitch + out_coff;
+  __syncthreads();
+  const int g = threadIdx.x & 15;                // column group: output columns 4g .. 4g+3
+  const int ly = threadIdx.x >> 4;               // output row within the CTA
+  float acc[4][16];
 #pragma unroll
-  for (int c = 0; c < 16; c += 4) {
-    float v[4];
+  for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = apply_act(acc[c + u], ACT_LEAKY);
-    store4(dst + c, v);
+    for (int c = 0; c < 16; ++c) acc[p][c] = sb[c];
+#pragma unroll
+  for (int kh = 0; kh < 5; ++kh) {
+    // input columns t = 8g-2 .. 8g+8  ->  tile columns 8g+2 .. 8g+12 ; load tile columns 8g .. 8g+12
+    const float* row = tile + (2 * ly + kh) * kC1Pitch + 8 * g;
+    float x[13];
+    const float4 a0 = *reinterpret_cast<const float4*>(row);
+    const float4 a1 = *reinterpret_cast<const float4*>(row + 4);
+    const float4 a2 = *reinterpret_cast<const float4*>(row + 8);
+    x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+    x[8] = a2.x; x[9] = a2.y; x[10] = a2.z; x[11] = a2.w; x[12] = row[12];
+#pragma unroll
+    for (int kw = 0; kw < 5; ++kw) {
+      const float4* wt = reinterpret_cast<const float4*>(sw + (kh * 5 + kw) * 16);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 wv = wt[c4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float xv = x[2 * p + kw + 2];     // tile column 8g + 2p + kw + 2  <->  t = 2(4g+p) + kw - 2
+          acc[p][4 * c4 + 0] = fmaf(xv, wv.x, acc[p][4 * c4 + 0]);
+          acc[p][4 * c4 + 1] = fmaf(xv, wv.y, acc[p][4 * c4 + 1]);
+          acc[p][4 * c4 + 2] = fmaf(xv, wv.z, acc[p][4 * c4 + 2]);
+          acc[p][4 * c4 + 3] = fmaf(xv, wv.w, acc[p][4 * c4 + 3]);
+        }
+      }
+    }
+  }
+  const int oh = oh0 + ly;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    T* dst = out + ((static_cast<size_t>(b) * 256 + oh) * 64 + 4 * g + p) * out_pitch + out_coff;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = apply_act(acc[p][c], act);
+    store16v(dst, v);                            // whole 32-byte sectors: no partial-sector writes in L2
   }
 }
 
@@ -146,7 +216,8 @@ template <typename T, bool kTransposed>
 __global__ void __launch_bounds__(256)
 conv_direct_kernel(const T* __restrict__ in, int in_pitch, int in_coff, int hin, int win, int cin,
                    const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-                   int out_pitch, int out_coff, int hout, int wout, int cout, int act, int batch) {
+                   int out_pitch, int out_coff, int hout, int wout, int cout, int act, int batch,
+                   int accumulate) {
   const int cg_n = cout >> 2;
   const size_t total = static_cast<size_t>(batch) * hout * wout * cg_n;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -157,7 +228,8 @@ conv_direct_kernel(const T* __restrict__ in, int in_pitch, int in_coff, int hin,
   const int oh = static_cast<int>(pix % hout);
   const int b = static_cast<int>(pix / hout);
   const int co = cg * 4;
-  float acc[4] = {bias[co], bias[co + 1], bias[co + 2], bias[co + 3]};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias) { acc[0] = bias[co]; acc[1] = bias[co + 1]; acc[2] = bias[co + 2]; acc[3] = bias[co + 3]; }
   for (int kh = 0; kh < 5; ++kh) {
     int ih;
     if (kTransposed) {                     // oh = 2 ih - 2 + kh
@@ -196,7 +268,12 @@ conv_direct_kernel(const T* __restrict__ in, int in_pitch, int in_coff, int hin,
   }
 #pragma unroll
   for (int u = 0; u < 4; ++u) acc[u] = apply_act(acc[u], act);
-  store4(out + ((static_cast<size_t>(b) * hout + oh) * wout + ow) * out_pitch + out_coff + co, acc);
+  T* dst = out + ((static_cast<size_t>(b) * hout + oh) * wout + ow) * out_pitch + out_coff + co;
+  if (accumulate) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] += to_float(dst[u]);
+  }
+  store4(dst, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,11 +349,11 @@ static int launch_layer_direct_t(const svs_unet_plan* plan, int li, const Worksp
                                  const int32_t* in_frames, int batch, int flags, cudaStream_t st) {
   const LayerGeom& g = kLayers[li];
   if (li == 0) {
-    dim3 grid(64 / 16, 256 / 16, batch);
-    conv1_kernel<T><<<grid, 256, 0, st>>>(in->base, in->patch_off, in->stride_b, in->stride_f, in->stride_t,
+    dim3 grid(256 / kC1Rows, batch);
+    conv1_kernel<T><<<grid, kC1Threads, 0, st>>>(in->base, in->patch_off, in->stride_b, in->stride_f, in->stride_t,
                                          in_frames, plan->w_fold[0], plan->b_fold[0],
                                          reinterpret_cast<T*>(ws.buf[g.out_buf]), kBufGeom[g.out_buf].c,
-                                         g.out_coff);
+                                         g.out_coff, ACT_LEAKY);
     SVS_CHECK_LAUNCH("conv1_kernel");
     return SVS_OK;
   }
@@ -297,14 +374,49 @@ static int launch_layer_direct_t(const svs_unet_plan* plan, int li, const Worksp
     conv_direct_kernel<T, true><<<blocks, 256, 0, st>>>(src, kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win,
                                                        g.cin, plan->w_fold[li], plan->b_fold[li], dst,
                                                        kBufGeom[g.out_buf].c, g.out_coff, g.hout, g.wout,
-                                                       g.cout, g.act, batch);
+                                                       g.cout, g.act, batch, 0);
   } else {
     conv_direct_kernel<T, false><<<blocks, 256, 0, st>>>(src, kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win,
                                                         g.cin, plan->w_fold[li], plan->b_fold[li], dst,
                                                         kBufGeom[g.out_buf].c, g.out_coff, g.hout, g.wout,
-                                                        g.cout, g.act, batch);
+                                                        g.cout, g.act, batch, 0);
   }
   SVS_CHECK_LAUNCH("conv_direct_kernel");
+  return SVS_OK;
+}
+
+// fp32 launchers used by the training step (train.cu)
+int launch_conv_direct_f32(const float* in, int in_pitch, int in_coff, int hin, int win, int cin, const float* w,
+                           const float* bias, float* out, int out_pitch, int out_coff, int hout, int wout,
+                           int cout, int act, bool transposed, int batch, bool accumulate, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(batch) * hout * wout * (cout / 4);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (transposed)
+    conv_direct_kernel<float, true><<<blocks, 256, 0, st>>>(in, in_pitch, in_coff, hin, win, cin, w, bias, out,
+                                                           out_pitch, out_coff, hout, wout, cout, act, batch,
+                                                           accumulate ? 1 : 0);
+  else
+    conv_direct_kernel<float, false><<<blocks, 256, 0, st>>>(in, in_pitch, in_coff, hin, win, cin, w, bias, out,
+                                                            out_pitch, out_coff, hout, wout, cout, act, batch,
+                                                            accumulate ? 1 : 0);
+  SVS_CHECK_LAUNCH("conv_direct_kernel");
+  return SVS_OK;
+}
+
+int launch_conv1_f32(const float* mix, const float* w, const float* bias, float* out, int batch, cudaStream_t st) {
+  dim3 grid(256 / kC1Rows, batch);
+  conv1_kernel<float><<<grid, kC1Threads, 0, st>>>(mix, nullptr, 512 * 128, 128, 1, nullptr, w, bias, out, 16, 0,
+                                                  ACT_NONE);
+  SVS_CHECK_LAUNCH("conv1_kernel");
+  return SVS_OK;
+}
+
+int launch_deconv6_f32(const float* cat1, const float* w, const float* bias, float* mask, int batch,
+                       cudaStream_t st) {
+  dim3 grid(128 / 16, 512 / 16, batch);
+  deconv6_kernel<float><<<grid, 256, 0, st>>>(cat1, w, bias, mask, nullptr, 512 * 128, 128, 1, mask, nullptr,
+                                             512 * 128, 128, 1, nullptr, 0);
+  SVS_CHECK_LAUNCH("deconv6_kernel");
   return SVS_OK;
 }
 

@@ -47,6 +47,7 @@ struct TcParams {
   int cout;                      // GEMM N (merged deconv: 4 x channels)
   int merged;                    // 1: N = 4 phases x cout_phase channels
   int cout_phase;
+  long long* dbg;                // optional per-CTA clock64 trace (8 slots per CTA), profiling only
 };
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -75,7 +76,8 @@ constexpr int kTcThreads = 192;
 
 template <int kBlockN, int kSwz, int kStages>
 constexpr size_t tc_smem_bytes() {
-  return static_cast<size_t>(kStages) * (128 + kBlockN) * kSwz + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  return static_cast<size_t>(kStages) * (128 + kBlockN) * kSwz + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+         2048 /*bias*/;
 }
 
 
@@ -106,6 +108,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 4));
+  float* sbias = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + 256);   // [bias_n] staged once
+  const int bias_n = p.merged ? p.cout_phase : p.cout;
+  for (int i = threadIdx.x; i < bias_n; i += kTcThreads) sbias[i] = __ldg(&p.bias[i]);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,6 +119,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int per_z = m_tiles * n_tiles;
   const int total_tiles = per_z * p.n_phases * p.split_k;
 
+  long long* dbg = p.dbg ? p.dbg + 8 * blockIdx.x : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
@@ -126,6 +133,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -155,6 +163,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
+    __syncwarp();                               // reconverge before the aligned block barrier below
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
@@ -175,6 +184,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int s = it % kStages;
           const uint32_t par = (it / kStages) & 1;
           mbar_wait(full_bar(s), par);
+          if (dbg && it == 0) dbg[2] = clock64();
           tc_fence_after();
           const uint32_t a_addr = smem_base + s * kStageBytes;
           const uint64_t da = make_smem_desc<kSwz>(a_addr);
@@ -187,8 +197,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
         }
         umma_commit(tmem_full_bar(as));         // accumulator complete
+        if (dbg && t == 0) dbg[3] = clock64();
       }
     }
+    __syncwarp();
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
@@ -211,33 +223,45 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool valid = b < p.batch;
       const int as = t & 1;
       mbar_wait(tmem_full_bar(as), (t >> 1) & 1);
+      if (dbg && t == 0 && threadIdx.x == 64) dbg[4] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccCols;
       if (p.split_k == 1) {
         OutT* const out_base = reinterpret_cast<OutT*>(p.out);
-#pragma unroll 1
-        for (int c = 0; c < kBlockN; c += 16) {
-          uint32_t v[16];
-          float f[16];
+        constexpr int kStep = kBlockN >= 32 ? 32 : 16;
+#pragma unroll 2
+        for (int c = 0; c < kBlockN; c += kStep) {
+          uint32_t v[kStep];
           if (n_iter > 0) {
-            tmem_ld16(taddr + c, v);
+            tmem_ld16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            if constexpr (kStep == 32) tmem_ld16(taddr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
             tmem_ld_wait();
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0u;
+            for (int i = 0; i < kStep; ++i) v[i] = 0u;
           }
-          // merged deconv: 16-column groups never straddle a phase (channels per phase >= 16)
-          int py = p.py[phase], px = p.px[phase], ch = n0 + c;
-          if (p.merged) {
-            const int ph = ch / p.cout_phase;
-            ch -= ph * p.cout_phase;
-            py = ph >> 1; px = ph & 1;
-          }
-          const int oy = gy * p.out_scale + py, ox = gx * p.out_scale + px;
-          OutT* dst = out_base + ((static_cast<size_t>(b) * p.hout + oy) * p.wout + ox) * p.out_pitch + p.out_coff + ch;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = tc_act(__uint_as_float(v[i]) + __ldg(&p.bias[ch + i]), p.act);
-          if (valid) store16(dst, f);
+          for (int h = 0; h < kStep; h += 16) {
+            // merged deconv: 16-column groups never straddle a phase (channels per phase >= 16)
+            int py = p.py[phase], px = p.px[phase], ch = n0 + c + h;
+            if (p.merged) {
+              const int ph = ch / p.cout_phase;
+              ch -= ph * p.cout_phase;
+              py = ph >> 1; px = ph & 1;
+            }
+            const int oy = gy * p.out_scale + py, ox = gx * p.out_scale + px;
+            OutT* dst = out_base + ((static_cast<size_t>(b) * p.hout + oy) * p.wout + ox) * p.out_pitch + p.out_coff + ch;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(&sbias[ch + i]);
+              f[i] = tc_act(__uint_as_float(v[h + i]) + bv.x, p.act);
+              f[i + 1] = tc_act(__uint_as_float(v[h + i + 1]) + bv.y, p.act);
+              f[i + 2] = tc_act(__uint_as_float(v[h + i + 2]) + bv.z, p.act);
+              f[i + 3] = tc_act(__uint_as_float(v[h + i + 3]) + bv.w, p.act);
+            }
+            if (valid) store16(dst, f);
+          }
         }
       } else {
         float* dst = p.partial +
@@ -261,10 +285,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(as));      // 4 warps -> accumulator stage is free
+      if (dbg && t == 0 && threadIdx.x == 64) dbg[5] = clock64();
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
@@ -588,6 +614,9 @@ static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p,
   return SVS_OK;
 }
 
+long long* g_tc_dbg = nullptr;   // set through svs_debug_set_trace (profiling only)
+int g_tc_dbg_layer = -1;
+
 int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st) {
   const TcLayer& t = plan->tc[li];
   const LayerGeom& g = kLayers[li];
@@ -633,6 +662,7 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   p.cout = t.merged ? 4 * g.cout : g.cout;
   p.merged = t.merged ? 1 : 0;
   p.cout_phase = g.cout;
+  p.dbg = (g_tc_dbg_layer == li) ? g_tc_dbg : nullptr;
   if (split > 1 && ws.splitk_bytes < static_cast<size_t>(split) * t.n_phases * p.m_pad * g.cout * sizeof(float))
     return fail(SVS_ERR_WORKSPACE, "tc_launch_layer: split-K scratch too small");
   p.m_tiles = m_tiles;
@@ -644,8 +674,8 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     rc = tf32 ? launch_tc<float, true, N, S, ST>(ta, t, p, grid, st)                                \
               : launch_tc<__nv_bfloat16, false, N, S, ST>(ta, t, p, grid, st);                      \
   }
-  SVS_TC_CASE(256, 128, 3)
-  SVS_TC_CASE(128, 128, 3)
+  SVS_TC_CASE(256, 128, 4)
+  SVS_TC_CASE(128, 128, 6)
   SVS_TC_CASE(64, 128, 4)
   SVS_TC_CASE(32, 128, 4)
   SVS_TC_CASE(16, 128, 4)
@@ -668,3 +698,9 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
 }
 
 }  // namespace svs
+
+extern "C" int svs_debug_set_trace(long long* device_buffer, int layer) {
+  svs::g_tc_dbg = device_buffer;
+  svs::g_tc_dbg_layer = device_buffer ? layer : -1;
+  return SVS_OK;
+}

@@ -1,15 +1,586 @@
-// T1: training step (train-mode forward, masked-L1 loss, backward) — see svs_b200.h.
-#include "svs_common.cuh"
+// T1: training step of the UNet — train-mode forward, masked-L1 loss, backward (svs_b200.h).
+//
+// Replaces the autograd graph of reference train.py:274-299 / model.py:203-220.  Activations are
+// fp32 NHWC in the same concat-buffer layout as the inference path; every reduction (BatchNorm
+// statistics, bias / BatchNorm gradients, weight gradients, the loss) is two-stage with a fixed order,
+// so a step is bit-reproducible (no atomics).  Convolutions run on the fp32 CUDA-core kernels of
+// conv_direct.cu:  dgrad of a stride-2 conv is the transposed-conv kernel with channel-transposed
+// weights, dgrad of a transposed conv is the conv kernel, wgrad is the pixel-reduction GEMM below.
+// (The tensor-core forward kernels are inference-only for now: see DESIGN.md "next".)
+#include "unet_internal.cuh"
 
-extern "C" size_t svs_unet_train_workspace_bytes(int batch) {
-  (void)batch;
-  return 0;
+namespace svs {
+
+int launch_conv_direct_f32(const float* in, int in_pitch, int in_coff, int hin, int win, int cin, const float* w,
+                           const float* bias, float* out, int out_pitch, int out_coff, int hout, int wout,
+                           int cout, int act, bool transposed, int batch, bool accumulate, cudaStream_t st);
+int launch_conv1_f32(const float* mix, const float* w, const float* bias, float* out, int batch, cudaStream_t st);
+int launch_deconv6_f32(const float* cat1, const float* w, const float* bias, float* mask, int batch,
+                       cudaStream_t st);
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+constexpr int kRedSplits = 64;                   // stage-1 partial sums per channel
+
+// torch layout -> [tap][ci][co]  (conv: (co,ci,kh,kw); deconv: (ci,co,kh,kw)) and its channel transpose
+__global__ void train_pack_kernel(const float* __restrict__ w, int cin, int cout, int transposed,
+                                  float* __restrict__ w_fwd /*[tap][ci][co]*/, float* __restrict__ w_t /*[tap][co][ci]*/) {
+  const int total = 25 * cin * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cout, ci = (i / cout) % cin, tap = i / (cout * cin);
+    const size_t src = transposed ? (static_cast<size_t>(ci) * cout + co) * 25 + tap
+                                  : (static_cast<size_t>(co) * cin + ci) * 25 + tap;
+    const float v = w[src];
+    w_fwd[i] = v;
+    w_t[(static_cast<size_t>(tap) * cout + co) * cin + ci] = v;
+  }
 }
 
-extern "C" int svs_unet_train_step(const svs_train_layer layers[12], const float* mix, const float* voc,
-                                   int batch, int two_term, int update_running_stats, float* loss_out,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
-  (void)layers; (void)mix; (void)voc; (void)batch; (void)two_term; (void)update_running_stats;
-  (void)loss_out; (void)workspace; (void)workspace_bytes; (void)stream;
-  return svs::fail(SVS_ERR_NOT_IMPLEMENTED, "svs_unet_train_step: not built yet (no fallback is provided)");
+// ---- per-channel reductions over an [N][C] fp32 slab (pitch / channel offset aware) ------------
+// mode 0: (sum z, sum z^2)                      BatchNorm statistics
+// mode 1: (sum g, sum g * xhat)  g = dy_eff     BatchNorm backward; dy_eff applies dropout and act'
+struct RedArgs {
+  const float* z;          // [N][C] pre-BN conv output
+  const float* y;          // activation buffer (post act/dropout), pitch/coff
+  const float* dy;         // gradient w.r.t. y, same pitch/coff
+  const uint8_t* keep;     // [B][C] or null
+  const float* mean; const float* invstd;
+  int y_pitch, y_coff, C, act, pix_per_sample;
+  size_t N;
+};
+
+__device__ __forceinline__ float dy_effective(const RedArgs& a, size_t n, int c) {
+  const float yv = a.y[n * a.y_pitch + a.y_coff + c];
+  float g = a.dy[n * a.y_pitch + a.y_coff + c];
+  if (a.keep) {
+    const int b = static_cast<int>(n / a.pix_per_sample);
+    g = a.keep[b * a.C + c] ? 2.0f * g : 0.0f;                 // Dropout2d(0.5): scale 1/(1-p)
+  }
+  if (a.act == ACT_RELU) g = yv > 0.0f ? g : 0.0f;
+  else if (a.act == ACT_LEAKY) g = yv > 0.0f ? g : 0.2f * g;
+  return g;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(256)
+channel_reduce_kernel(RedArgs a, float* __restrict__ partial /*[splits][2][C]*/) {
+  __shared__ float s0[8][32], s1[8][32];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const size_t per = (a.N + gridDim.y - 1) / gridDim.y;
+  const size_t n0 = blockIdx.y * per, n1 = min(a.N, n0 + per);
+  float acc0 = 0.f, acc1 = 0.f;
+  if (c < a.C) {
+    for (size_t n = n0 + ty; n < n1; n += 8) {
+      if (kMode == 0) {
+        const float v = a.z[n * a.C + c];
+        acc0 += v; acc1 += v * v;
+      } else {
+        const float g = dy_effective(a, n, c);
+        const float xh = (a.z[n * a.C + c] - a.mean[c]) * a.invstd[c];
+        acc0 += g; acc1 += g * xh;
+      }
+    }
+  }
+  s0[ty][cx] = acc0; s1[ty][cx] = acc1;
+  __syncthreads();
+  if (ty == 0 && c < a.C) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0 += s0[i][cx]; t1 += s1[i][cx]; }
+    partial[(static_cast<size_t>(blockIdx.y) * 2 + 0) * a.C + c] = t0;
+    partial[(static_cast<size_t>(blockIdx.y) * 2 + 1) * a.C + c] = t1;
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int splits, int C, double n,
+                                   float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, int update) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int i = 0; i < splits; ++i) { s += partial[(i * 2 + 0) * C + c]; ss += partial[(i * 2 + 1) * C + c]; }
+  const double m = s / n;
+  double var = ss / n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = static_cast<float>(m);
+  invstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
+  if (update && running_mean) {                                  // torch: momentum 0.1, unbiased variance
+    running_mean[c] = (1.0f - kBnMomentum) * running_mean[c] + kBnMomentum * static_cast<float>(m);
+    running_var[c] = (1.0f - kBnMomentum) * running_var[c] + kBnMomentum * static_cast<float>(var * n / (n - 1.0));
+  }
+}
+
+// y = dropout(act(gamma * (z - mean) * invstd + beta)) -> concat buffer
+__global__ void bn_apply_kernel(const float* __restrict__ z, size_t N, int C, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const uint8_t* __restrict__ keep,
+                                int pix_per_sample, int act, float* __restrict__ y, int y_pitch, int y_coff) {
+  const size_t total = N * C;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t n = i / C;
+    float v = (z[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+    if (act == ACT_LEAKY) v = v > 0.f ? v : 0.2f * v;
+    else if (act == ACT_RELU) v = fmaxf(v, 0.f);
+    if (keep) v = keep[(n / pix_per_sample) * C + c] ? 2.0f * v : 0.0f;
+    y[n * y_pitch + y_coff + c] = v;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int splits, int C,
+                                       float* __restrict__ sum_g, float* __restrict__ sum_gx,
+                                       float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
+                                       float* __restrict__ grad_conv_bias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int i = 0; i < splits; ++i) { s += partial[(i * 2 + 0) * C + c]; sx += partial[(i * 2 + 1) * C + c]; }
+  sum_g[c] = static_cast<float>(s);
+  sum_gx[c] = static_cast<float>(sx);
+  grad_beta[c] = static_cast<float>(s);
+  grad_gamma[c] = static_cast<float>(sx);
+  grad_conv_bias[c] = 0.0f;      // d/d(bias) of a conv feeding a batch-stat BatchNorm is identically zero
+}
+
+// dz = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)), written in place over z
+__global__ void bn_bwd_apply_kernel(RedArgs a, const float* __restrict__ gamma, const float* __restrict__ sum_g,
+                                    const float* __restrict__ sum_gx, float* __restrict__ z_inout) {
+  const size_t total = a.N * a.C;
+  const float inv_n = 1.0f / static_cast<float>(a.N);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % a.C);
+    const size_t n = i / a.C;
+    const float g = dy_effective(a, n, c);
+    const float xh = (z_inout[i] - a.mean[c]) * a.invstd[c];
+    z_inout[i] = gamma[c] * a.invstd[c] * (g - sum_g[c] * inv_n - xh * sum_gx[c] * inv_n);
+  }
+}
+
+// ---- weight gradient: dW[tap][ci][co] = sum over pixels of the small grid -----------------------
+// S = tensor living on the small grid (conv: dY, deconv: X), L = tensor on the 2x grid (conv: X,
+// deconv: dY); pixel (gy, gx) of S pairs with (2gy + kh - 2, 2gx + kw - 2) of L.
+struct WgradArgs {
+  const float* S; int s_pitch, s_coff, s_c;
+  const float* L; int l_pitch, l_coff, l_c;
+  int gh, gw, batch;          // small grid
+  int s_is_cout;              // 1: conv (S = dY -> co, L = X -> ci); 0: deconv (S = X -> ci, L = dY -> co)
+  int cin, cout;
+};
+
+__global__ void __launch_bounds__(64)
+wgrad_kernel(WgradArgs a, float* __restrict__ partial /*[splits][25][cin][cout]*/) {
+  __shared__ __align__(16) float ss[16][32], sl[16][32];
+  const int tap = blockIdx.x;
+  const int kh = tap / 5, kw = tap % 5;
+  const int co_tiles = (a.cout + 31) / 32;
+  const int ci0 = (blockIdx.y / co_tiles) * 32, co0 = (blockIdx.y % co_tiles) * 32;
+  const int s0 = a.s_is_cout ? co0 : ci0, l0 = a.s_is_cout ? ci0 : co0;
+  const size_t npix = static_cast<size_t>(a.batch) * a.gh * a.gw;
+  const size_t per = (npix + gridDim.z - 1) / gridDim.z;
+  const size_t p_begin = blockIdx.z * per, p_end = min(npix, p_begin + per);
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;      // thread tile: 4 (ci) x 4 (co)
+  float acc[4][4] = {};
+  const int lh = 2 * a.gh, lw = 2 * a.gw;
+  for (size_t p0 = p_begin; p0 < p_end; p0 += 16) {
+    // stage 16 pixels x 32 channels of S and of L (zero where out of range)
+    for (int i = threadIdx.x; i < 16 * 32; i += 64) {
+      const int r = i >> 5, c = i & 31;
+      const size_t p = p0 + r;
+      float vs = 0.f, vl = 0.f;
+      if (p < p_end) {
+        const int gx = static_cast<int>(p % a.gw);
+        const int gy = static_cast<int>((p / a.gw) % a.gh);
+        const int b = static_cast<int>(p / (static_cast<size_t>(a.gw) * a.gh));
+        if (s0 + c < a.s_c) vs = a.S[p * a.s_pitch + a.s_coff + s0 + c];
+        const int ly = 2 * gy + kh - 2, lx = 2 * gx + kw - 2;
+        if (ly >= 0 && ly < lh && lx >= 0 && lx < lw && l0 + c < a.l_c)
+          vl = a.L[((static_cast<size_t>(b) * lh + ly) * lw + lx) * a.l_pitch + a.l_coff + l0 + c];
+      }
+      ss[r][c] = vs; sl[r][c] = vl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float4 vci = *reinterpret_cast<const float4*>(a.s_is_cout ? &sl[r][4 * ty] : &ss[r][4 * ty]);
+      const float4 vco = *reinterpret_cast<const float4*>(a.s_is_cout ? &ss[r][4 * tx] : &sl[r][4 * tx]);
+      const float xi[4] = {vci.x, vci.y, vci.z, vci.w}, yo[4] = {vco.x, vco.y, vco.z, vco.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xi[i], yo[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dst = partial + (static_cast<size_t>(blockIdx.z) * 25 + tap) * a.cin * a.cout;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + 4 * ty + i, co = co0 + 4 * tx + j;
+      if (ci < a.cin && co < a.cout) dst[static_cast<size_t>(ci) * a.cout + co] = acc[i][j];
+    }
+}
+
+// sum the split partials (fixed order) and scatter to the torch layout
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
+                                      int transposed, float* __restrict__ grad_w) {
+  const int total = 25 * cin * cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[static_cast<size_t>(k) * total + i];
+    const int co = i % cout, ci = (i / cout) % cin, tap = i / (cout * cin);
+    const size_t dst = transposed ? (static_cast<size_t>(ci) * cout + co) * 25 + tap
+                                  : (static_cast<size_t>(co) * cin + ci) * 25 + tap;
+    grad_w[dst] = s;
+  }
+}
+
+// ---- deconv6 / loss ------------------------------------------------------------------------------
+// dz6 = grad_mask * m * (1 - m)   (sigmoid backward, in place over the grad buffer)
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ mask, const float* __restrict__ grad_mask, size_t n,
+                                   float* __restrict__ dz) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float m = mask[i];
+    dz[i] = grad_mask[i] * m * (1.0f - m);
+  }
+}
+
+// dX[b,ih,iw,ci] = sum_taps dz6[b, 2ih-2+kh, 2iw-2+kw] * w6[ci][tap]   (dgrad of ConvTranspose2d(32 -> 1))
+__global__ void deconv6_dgrad_kernel(const float* __restrict__ dz /*[B][512][128]*/, const float* __restrict__ w /*[25][32]*/,
+                                     float* __restrict__ dx /*[B][256][64][32]*/, int batch) {
+  __shared__ float sw[25 * 32];
+  for (int i = threadIdx.x; i < 800; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const size_t total = static_cast<size_t>(batch) * 256 * 64 * 8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = static_cast<int>(idx & 7);
+  const size_t pix = idx >> 3;
+  const int iw = static_cast<int>(pix % 64), ih = static_cast<int>((pix / 64) % 256);
+  const int b = static_cast<int>(pix / (64 * 256));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kh = 0; kh < 5; ++kh) {
+    const int oh = 2 * ih - 2 + kh;
+    if (oh < 0 || oh >= 512) continue;
+    for (int kw = 0; kw < 5; ++kw) {
+      const int ow = 2 * iw - 2 + kw;
+      if (ow < 0 || ow >= 128) continue;
+      const float g = dz[(static_cast<size_t>(b) * 512 + oh) * 128 + ow];
+      const float* wt = sw + (kh * 5 + kw) * 32 + 4 * cg;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(g, wt[u], acc[u]);
+    }
+  }
+  *reinterpret_cast<float4*>(dx + pix * 32 + 4 * cg) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// generic fixed-order sum of an array -> one float (used for deconv6's bias gradient and the loss terms)
+__global__ void __launch_bounds__(256) sum_stage1_kernel(const float* __restrict__ x, size_t n, float* __restrict__ partial) {
+  __shared__ float s[256];
+  const size_t per = (n + gridDim.x - 1) / gridDim.x;
+  const size_t a = blockIdx.x * per, b = min(n, a + per);
+  float acc = 0.f;
+  for (size_t i = a + threadIdx.x; i < b; i += 256) acc += x[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+__global__ void sum_stage2_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += partial[i];
+  *out = static_cast<float>(s * scale);
+}
+
+// L = mean|m x - v| + mean|(1-m) x - max(x - v, 0)| ; grad wrt m
+__global__ void __launch_bounds__(256)
+l1_loss_kernel(const float* __restrict__ mask, const float* __restrict__ mix, const float* __restrict__ voc,
+               size_t n, int two_term, float gscale, float* __restrict__ partial /*[grid][2]*/,
+               float* __restrict__ grad_mask) {
+  __shared__ float sv[256], sa[256];
+  const size_t per = (n + gridDim.x - 1) / gridDim.x;
+  const size_t a = blockIdx.x * per, b = min(n, a + per);
+  float lv = 0.f, la = 0.f;
+  for (size_t i = a + threadIdx.x; i < b; i += 256) {
+    const float m = mask[i], x = mix[i], v = voc[i];
+    const float dv = m * x - v;
+    lv += fabsf(dv);
+    float g = (dv > 0.f ? 1.f : (dv < 0.f ? -1.f : 0.f)) * x;         // torch: sign(0) = 0
+    if (two_term) {
+      const float da = (1.0f - m) * x - fmaxf(x - v, 0.0f);
+      la += fabsf(da);
+      g -= (da > 0.f ? 1.f : (da < 0.f ? -1.f : 0.f)) * x;
+    }
+    if (grad_mask) grad_mask[i] = g * gscale;
+  }
+  sv[threadIdx.x] = lv; sa[threadIdx.x] = la;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sv[threadIdx.x] += sv[threadIdx.x + o]; sa[threadIdx.x] += sa[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sv[0]; partial[2 * blockIdx.x + 1] = sa[0]; }
+}
+__global__ void l1_loss_finalize_kernel(const float* __restrict__ partial, int blocks, double n, float* __restrict__ out) {
+  double v = 0.0, a = 0.0;
+  for (int i = 0; i < blocks; ++i) { v += partial[2 * i]; a += partial[2 * i + 1]; }
+  out[1] = static_cast<float>(v / n);
+  out[2] = static_cast<float>(a / n);
+  out[0] = static_cast<float>(v / n + a / n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+struct TrainWs {
+  float* cat[BUF_COUNT];      // activations (post BN / act / dropout), concat layout
+  float* dcat[BUF_COUNT];     // gradients w.r.t. the same buffers
+  float* z[12];               // pre-BN conv outputs (z[11] unused: the mask lives in the caller's tensor)
+  float* dz6;                 // [B][512][128]
+  float* w_fwd[12]; float* w_t[12];
+  float* mean[12]; float* invstd[12]; float* sum_g[12]; float* sum_gx[12];
+  float* red_partial;         // [kRedSplits][2][512]
+  float* wgrad_partial;
+  size_t wgrad_partial_floats;
+  float* scalar_partial;      // [1024 * 2]
+  size_t total;
+};
+
+static int wgrad_splits(int li, int batch) {
+  const LayerGeom& g = kLayers[li];
+  const int gh = g.transposed ? g.hin : g.hout, gw = g.transposed ? g.win : g.wout;
+  const size_t npix = static_cast<size_t>(batch) * gh * gw;
+  const int tiles = 25 * ((g.cin + 31) / 32) * ((g.cout + 31) / 32);
+  int s = (148 * 16 + tiles - 1) / tiles;                        // ~16 CTAs of 64 threads per SM
+  const size_t max_s = (npix + 255) / 256;                       // at least 256 pixels per split
+  if (static_cast<size_t>(s) > max_s) s = static_cast<int>(max_s);
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  return s;
+}
+
+static TrainWs carve_train(char* base, int batch) {
+  TrainWs w{};
+  size_t off = 0;
+  auto take = [&](size_t floats) {
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += (floats * sizeof(float) + 255) / 256 * 256;
+    return p;
+  };
+  for (int i = 0; i < BUF_COUNT; ++i) {
+    const size_t n = static_cast<size_t>(batch) * kBufGeom[i].h * kBufGeom[i].w * kBufGeom[i].c;
+    w.cat[i] = take(n);
+    w.dcat[i] = take(n);
+  }
+  size_t wg = 0;
+  for (int li = 0; li < 12; ++li) {
+    const LayerGeom& g = kLayers[li];
+    w.z[li] = li < 11 ? take(static_cast<size_t>(batch) * g.hout * g.wout * g.cout) : nullptr;
+    w.w_fwd[li] = take(static_cast<size_t>(25) * g.cin * g.cout);
+    w.w_t[li] = take(static_cast<size_t>(25) * g.cin * g.cout);
+    w.mean[li] = take(g.cout); w.invstd[li] = take(g.cout); w.sum_g[li] = take(g.cout); w.sum_gx[li] = take(g.cout);
+    const size_t need = static_cast<size_t>(wgrad_splits(li, batch)) * 25 * g.cin * g.cout;
+    wg = need > wg ? need : wg;
+  }
+  w.dz6 = take(static_cast<size_t>(batch) * 512 * 128);
+  w.red_partial = take(static_cast<size_t>(kRedSplits) * 2 * 512);
+  w.wgrad_partial = take(wg);
+  w.wgrad_partial_floats = wg;
+  w.scalar_partial = take(2048);
+  w.total = off;
+  return w;
+}
+
+static unsigned grid_for(size_t n) {
+  size_t b = (n + 255) / 256;
+  return static_cast<unsigned>(b > 148 * 32 ? 148 * 32 : (b ? b : 1));
+}
+
+}  // namespace svs
+
+using namespace svs;
+
+extern "C" size_t svs_unet_train_workspace_bytes(int batch) {
+  if (batch <= 0) return 0;
+  return carve_train(nullptr, batch).total;
+}
+
+static int check_train_args(const svs_train_layer layers[12], const void* mix, int batch, void* workspace,
+                            size_t workspace_bytes) {
+  SVS_REQUIRE(layers && mix && workspace, "svs_unet_train: null pointer");
+  SVS_REQUIRE(batch > 1, "svs_unet_train: batch must be > 1 (batch-statistic BatchNorm)");
+  SVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "svs_unet_train: workspace must be 256-byte aligned");
+  for (int i = 0; i < 12; ++i) {
+    SVS_REQUIRE(layers[i].weight && layers[i].bias, "svs_unet_train: weight/bias missing");
+    SVS_REQUIRE((layers[i].bn_weight != nullptr) == (i != 11), "svs_unet_train: BatchNorm on every block but deconv6");
+  }
+  if (workspace_bytes < carve_train(nullptr, batch).total)
+    return fail(SVS_ERR_WORKSPACE, "svs_unet_train: workspace too small");
+  return SVS_OK;
+}
+
+extern "C" int svs_unet_train_forward(const svs_train_layer layers[12], const float* mix, int batch,
+                                      int update_running_stats, float* mask_out, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  int rc = check_train_args(layers, mix, batch, workspace, workspace_bytes);
+  if (rc != SVS_OK) return rc;
+  SVS_REQUIRE(mask_out, "svs_unet_train_forward: null mask_out");
+  int dev = 0;
+  SVS_CUDA_TRY(cudaGetDevice(&dev));
+  rc = svs_device_check(dev);
+  if (rc != SVS_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TrainWs w = carve_train(static_cast<char*>(workspace), batch);
+  for (int li = 0; li < 12; ++li) {
+    const LayerGeom& g = kLayers[li];
+    const svs_train_layer& L = layers[li];
+    train_pack_kernel<<<grid_for(25 * g.cin * g.cout), 256, 0, st>>>(L.weight, g.cin, g.cout, g.transposed ? 1 : 0,
+                                                                    w.w_fwd[li], w.w_t[li]);
+    SVS_CHECK_LAUNCH("train_pack_kernel");
+    if (li == 11) {                                                // deconv6 + sigmoid -> mask
+      rc = launch_deconv6_f32(w.cat[BUF_CAT1], w.w_fwd[11], L.bias, mask_out, batch, st);
+      if (rc != SVS_OK) return rc;
+      break;
+    }
+    if (li == 0) rc = launch_conv1_f32(mix, w.w_fwd[0], L.bias, w.z[0], batch, st);
+    else rc = launch_conv_direct_f32(w.cat[g.in_buf], kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win, g.cin,
+                                     w.w_fwd[li], L.bias, w.z[li], g.cout, 0, g.hout, g.wout, g.cout, ACT_NONE,
+                                     g.transposed, batch, false, st);
+    if (rc != SVS_OK) return rc;
+    const size_t N = static_cast<size_t>(batch) * g.hout * g.wout;
+    RedArgs a{};
+    a.z = w.z[li]; a.C = g.cout; a.N = N;
+    dim3 rgrid((g.cout + 31) / 32, kRedSplits);
+    channel_reduce_kernel<0><<<rgrid, 256, 0, st>>>(a, w.red_partial);
+    SVS_CHECK_LAUNCH("channel_reduce_kernel<0>");
+    bn_finalize_kernel<<<(g.cout + 127) / 128, 128, 0, st>>>(w.red_partial, kRedSplits, g.cout, static_cast<double>(N),
+                                                            w.mean[li], w.invstd[li], L.bn_running_mean,
+                                                            L.bn_running_var, update_running_stats);
+    SVS_CHECK_LAUNCH("bn_finalize_kernel");
+    bn_apply_kernel<<<grid_for(N * g.cout), 256, 0, st>>>(w.z[li], N, g.cout, w.mean[li], w.invstd[li], L.bn_weight,
+                                                         L.bn_bias, L.dropout_keep, g.hout * g.wout, g.act,
+                                                         w.cat[g.out_buf], kBufGeom[g.out_buf].c, g.out_coff);
+    SVS_CHECK_LAUNCH("bn_apply_kernel");
+  }
+  return SVS_OK;
+}
+
+namespace svs {
+static int run_wgrad(const TrainWs& w, const svs_train_layer& L, int li, int batch, const float* dY, int dy_pitch,
+                     int dy_coff, const float* X, int x_pitch, int x_coff, cudaStream_t st) {
+  const LayerGeom& g = kLayers[li];
+  WgradArgs a{};
+  a.cin = g.cin; a.cout = g.cout; a.batch = batch;
+  if (!g.transposed) {             // conv: small grid = output (dY), large = input (X)
+    a.S = dY; a.s_pitch = dy_pitch; a.s_coff = dy_coff; a.s_c = g.cout;
+    a.L = X; a.l_pitch = x_pitch; a.l_coff = x_coff; a.l_c = g.cin;
+    a.gh = g.hout; a.gw = g.wout; a.s_is_cout = 1;
+  } else {                         // deconv: small grid = input (X), large = output (dY)
+    a.S = X; a.s_pitch = x_pitch; a.s_coff = x_coff; a.s_c = g.cin;
+    a.L = dY; a.l_pitch = dy_pitch; a.l_coff = dy_coff; a.l_c = g.cout;
+    a.gh = g.hin; a.gw = g.win; a.s_is_cout = 0;
+  }
+  const int splits = wgrad_splits(li, batch);
+  dim3 grid(25, ((g.cin + 31) / 32) * ((g.cout + 31) / 32), splits);
+  wgrad_kernel<<<grid, 64, 0, st>>>(a, w.wgrad_partial);
+  SVS_CHECK_LAUNCH("wgrad_kernel");
+  wgrad_finalize_kernel<<<grid_for(25 * g.cin * g.cout), 256, 0, st>>>(w.wgrad_partial, splits, g.cin, g.cout,
+                                                                      g.transposed ? 1 : 0, L.grad_weight);
+  SVS_CHECK_LAUNCH("wgrad_finalize_kernel");
+  return SVS_OK;
+}
+}  // namespace svs
+
+extern "C" int svs_unet_train_backward(const svs_train_layer layers[12], const float* mix, const float* grad_mask,
+                                       int batch, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_train_args(layers, mix, batch, workspace, workspace_bytes);
+  if (rc != SVS_OK) return rc;
+  SVS_REQUIRE(grad_mask, "svs_unet_train_backward: null grad_mask");
+  for (int i = 0; i < 12; ++i) {
+    SVS_REQUIRE(layers[i].grad_weight && layers[i].grad_bias, "svs_unet_train_backward: grad buffers missing");
+    if (i != 11) SVS_REQUIRE(layers[i].grad_bn_weight && layers[i].grad_bn_bias, "svs_unet_train_backward: BN grad buffers missing");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TrainWs w = carve_train(static_cast<char*>(workspace), batch);
+  // ---- deconv6: sigmoid backward, bias / weight gradient, data gradient into dcat1 (all 32 channels) ----
+  // the mask is recomputed from the forward's output held by the caller? No: m(1-m) needs the mask; the
+  // forward wrote it to mask_out only, so dz6 is formed from grad_mask and the mask re-derived here.
+  {
+    const size_t n = static_cast<size_t>(batch) * 512 * 128;
+    // recompute the mask into dz6 (deterministic: same kernel, same inputs), then dz6 <- grad * m (1 - m)
+    rc = launch_deconv6_f32(w.cat[BUF_CAT1], w.w_fwd[11], layers[11].bias, w.dz6, batch, st);
+    if (rc != SVS_OK) return rc;
+    sigmoid_bwd_kernel<<<grid_for(n), 256, 0, st>>>(w.dz6, grad_mask, n, w.dz6);
+    SVS_CHECK_LAUNCH("sigmoid_bwd_kernel");
+    sum_stage1_kernel<<<1024, 256, 0, st>>>(w.dz6, n, w.scalar_partial);
+    SVS_CHECK_LAUNCH("sum_stage1_kernel");
+    sum_stage2_kernel<<<1, 1, 0, st>>>(w.scalar_partial, 1024, 1.0f, layers[11].grad_bias);
+    SVS_CHECK_LAUNCH("sum_stage2_kernel");
+    rc = run_wgrad(w, layers[11], 11, batch, w.dz6, 1, 0, w.cat[BUF_CAT1], 32, 0, st);
+    if (rc != SVS_OK) return rc;
+    const size_t threads = static_cast<size_t>(batch) * 256 * 64 * 8;
+    deconv6_dgrad_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(w.dz6, w.w_fwd[11],
+                                                                                      w.dcat[BUF_CAT1], batch);
+    SVS_CHECK_LAUNCH("deconv6_dgrad_kernel");
+  }
+  // ---- deconv5 .. deconv1, conv6 .. conv1 ----
+  for (int li = 10; li >= 0; --li) {
+    const LayerGeom& g = kLayers[li];
+    const svs_train_layer& L = layers[li];
+    const size_t N = static_cast<size_t>(batch) * g.hout * g.wout;
+    RedArgs a{};
+    a.z = w.z[li]; a.C = g.cout; a.N = N;
+    a.y = w.cat[g.out_buf]; a.dy = w.dcat[g.out_buf];
+    a.y_pitch = kBufGeom[g.out_buf].c; a.y_coff = g.out_coff;
+    a.keep = L.dropout_keep; a.mean = w.mean[li]; a.invstd = w.invstd[li];
+    a.act = g.act; a.pix_per_sample = g.hout * g.wout;
+    dim3 rgrid((g.cout + 31) / 32, kRedSplits);
+    channel_reduce_kernel<1><<<rgrid, 256, 0, st>>>(a, w.red_partial);
+    SVS_CHECK_LAUNCH("channel_reduce_kernel<1>");
+    bn_bwd_finalize_kernel<<<(g.cout + 127) / 128, 128, 0, st>>>(w.red_partial, kRedSplits, g.cout, w.sum_g[li],
+                                                                w.sum_gx[li], L.grad_bn_weight, L.grad_bn_bias,
+                                                                L.grad_bias);
+    SVS_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+    bn_bwd_apply_kernel<<<grid_for(N * g.cout), 256, 0, st>>>(a, L.bn_weight, w.sum_g[li], w.sum_gx[li], w.z[li]);
+    SVS_CHECK_LAUNCH("bn_bwd_apply_kernel");
+    // now z[li] holds dz (gradient w.r.t. the conv output)
+    const float* X = li == 0 ? mix : w.cat[g.in_buf];
+    const int x_pitch = li == 0 ? 1 : kBufGeom[g.in_buf].c;
+    rc = run_wgrad(w, L, li, batch, w.z[li], g.cout, 0, X, x_pitch, g.in_coff, st);
+    if (rc != SVS_OK) return rc;
+    if (li == 0) break;                                            // the mixture needs no gradient
+    // data gradient into dcat[in_buf][in_coff .. in_coff + cin): conv dgrad = transposed kernel, deconv dgrad =
+    // conv kernel, both with channel-transposed weights.  Encoder layers ACCUMULATE into the skip half that the
+    // decoder consumer has already written (decoder layers run first in this loop).
+    const bool accumulate = !g.transposed;
+    rc = launch_conv_direct_f32(w.z[li], g.cout, 0, g.hout, g.wout, g.cout, w.w_t[li], nullptr, w.dcat[g.in_buf],
+                                kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win, g.cin, ACT_NONE, !g.transposed, batch,
+                                accumulate, st);
+    if (rc != SVS_OK) return rc;
+  }
+  return SVS_OK;
+}
+
+extern "C" int svs_l1_masked_loss(const float* mask, const float* mix, const float* voc, int64_t n, int two_term,
+                                  float grad_scale, float* loss_out, float* grad_mask_out, void* stream) {
+  SVS_REQUIRE(mask && mix && voc && loss_out && n > 0, "svs_l1_masked_loss: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // partial sums live at the tail of loss_out? No: the caller provides only 3 floats, so use a static
+  // per-device scratch allocated once.
+  static float* scratch[64] = {};
+  int dev = 0;
+  SVS_CUDA_TRY(cudaGetDevice(&dev));
+  if (!scratch[dev]) SVS_CUDA_TRY(cudaMalloc(&scratch[dev], sizeof(float) * 2 * 1024));
+  l1_loss_kernel<<<1024, 256, 0, st>>>(mask, mix, voc, static_cast<size_t>(n), two_term, grad_scale / static_cast<float>(n),
+                                       scratch[dev], grad_mask_out);
+  SVS_CHECK_LAUNCH("l1_loss_kernel");
+  l1_loss_finalize_kernel<<<1, 1, 0, st>>>(scratch[dev], 1024, static_cast<double>(n), loss_out);
+  SVS_CHECK_LAUNCH("l1_loss_finalize_kernel");
+  return SVS_OK;
 }

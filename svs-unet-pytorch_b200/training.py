@@ -1,0 +1,217 @@
+"""Training step on the sm_100a kernels (reference train.py:265-300).
+
+* ``train_forward(model, mix)`` is what ``UNet.forward`` calls in ``train()`` mode: an autograd
+  Function whose forward is ``svs_unet_train_forward`` (batch-statistic BatchNorm, running-stat update,
+  Dropout2d through explicit keep masks) and whose backward is ``svs_unet_train_backward``; the torch
+  loss code of reference train.py:275-299 works on the returned mask unchanged.
+* ``train_step(model, mix, voc)`` is the fused fast path: forward, ``svs_l1_masked_loss`` (loss + dL/dmask
+  in one kernel), backward, one flat-buffer gradient all-reduce over NCCL when ``torch.distributed`` is
+  initialised (data parallel, reference has none), then ``model.optim.step()`` (Adam, model.py:116).
+There is no CPU path."""
+from __future__ import annotations
+
+from ctypes import byref
+
+import torch
+
+from . import _lib
+
+_LAYERS = ["conv1", "conv2", "conv3", "conv4", "conv5", "conv6",
+           "deconv1", "deconv2", "deconv3", "deconv4", "deconv5", "deconv6"]
+
+
+def _layer_modules(model, i):
+    name = _LAYERS[i]
+    if i < 6:
+        seq = getattr(model, name)
+        return seq[0], seq[1], None
+    conv = getattr(model, name)
+    if i == 11:
+        return conv, None, None
+    bad = getattr(model, name + "_BAD")
+    return conv, bad[0], bad[2]
+
+
+def param_list(model):
+    """The 46 trainable tensors in the order the C ABI's svs_train_layer array uses."""
+    out = []
+    for i in range(12):
+        conv, bn, _ = _layer_modules(model, i)
+        out += [conv.weight, conv.bias]
+        if bn is not None:
+            out += [bn.weight, bn.bias]
+    return out
+
+
+def _workspace(model, batch):
+    ws = getattr(model, "_train_ws", None)
+    if ws is None or ws[0] != batch:
+        nbytes = _lib.load().svs_unet_train_workspace_bytes(batch)
+        dev = next(model.parameters()).device
+        raw = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-raw.data_ptr()) % 256
+        model._train_ws = (batch, raw[off:off + nbytes])
+    return model._train_ws[1]
+
+
+def _flat_grads(model):
+    fg = getattr(model, "_flat_grad", None)
+    n = sum(p.numel() for p in param_list(model))
+    dev = next(model.parameters()).device
+    if fg is None or fg.numel() != n or fg.device != dev:
+        model._flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+    views, off = [], 0
+    for p in param_list(model):
+        views.append(model._flat_grad[off:off + p.numel()].view_as(p))
+        off += p.numel()
+    return model._flat_grad, views
+
+
+def dropout_masks(model, batch, injected=None):
+    """Per decoder block keep masks uint8 (B, C) — Dropout2d zeroes whole channels (model.py:83)."""
+    masks = {}
+    dev = next(model.parameters()).device
+    for i in range(6, 11):
+        name = _LAYERS[i]
+        _, bn, drop = _layer_modules(model, i)
+        if injected is not None and name in injected:
+            masks[name] = injected[name].to(device=dev, dtype=torch.uint8).contiguous()
+            continue
+        p = float(drop.p)
+        if p == 0.0:
+            continue
+        if abs(p - 0.5) > 1e-12:
+            raise _lib.SvsError("the training kernels implement Dropout2d(p=0.5) (reference model.py:83) or p=0")
+        masks[name] = (torch.rand(batch, bn.num_features, device=dev) >= 0.5).to(torch.uint8)
+    return masks
+
+
+def _layer_structs(model, grads, masks, need_grads=True):
+    arr = (_lib.TrainLayer * 12)()
+    gi = 0
+    for i in range(12):
+        conv, bn, _ = _layer_modules(model, i)
+        arr[i].weight = conv.weight.data_ptr()
+        arr[i].bias = conv.bias.data_ptr()
+        if need_grads:
+            arr[i].grad_weight = grads[gi].data_ptr()
+            arr[i].grad_bias = grads[gi + 1].data_ptr()
+        gi += 2
+        if bn is not None:
+            arr[i].bn_weight = bn.weight.data_ptr()
+            arr[i].bn_bias = bn.bias.data_ptr()
+            arr[i].bn_running_mean = bn.running_mean.data_ptr()
+            arr[i].bn_running_var = bn.running_var.data_ptr()
+            if need_grads:
+                arr[i].grad_bn_weight = grads[gi].data_ptr()
+                arr[i].grad_bn_bias = grads[gi + 1].data_ptr()
+            gi += 2
+        m = masks.get(_LAYERS[i]) if masks else None
+        if m is not None:
+            arr[i].dropout_keep = m.data_ptr()
+    return arr
+
+
+def _check_inputs(model, mix):
+    _lib.require_cuda(mix, "mix", torch.float32)
+    if mix.dim() != 4 or tuple(mix.shape[1:]) != (1, 512, 128):
+        raise _lib.SvsError(f"mix must have shape (B, 1, 512, 128); got {tuple(mix.shape)}")
+    for p in param_list(model):
+        _lib.require_cuda(p, "parameter", torch.float32)
+        if not p.is_contiguous():
+            raise _lib.SvsError("parameters must be contiguous")
+    _lib.check_device(mix.device)
+
+
+def _raw_forward(model, mix, masks, update_running=True):
+    b = mix.shape[0]
+    ws = _workspace(model, b)
+    arr = _layer_structs(model, None, masks, need_grads=False)
+    mask = torch.empty_like(mix)
+    with torch.cuda.device(mix.device):
+        _lib.check(_lib.load().svs_unet_train_forward(arr, mix.data_ptr(), b, 1 if update_running else 0,
+                                                      mask.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                      _lib.stream_ptr(mix.device)), "svs_unet_train_forward")
+    if update_running:
+        for i in range(11):
+            _, bn, _ = _layer_modules(model, i)
+            bn.num_batches_tracked += 1
+    return mask
+
+
+def _raw_backward(model, mix, grad_mask, masks, grads):
+    b = mix.shape[0]
+    ws = _workspace(model, b)
+    arr = _layer_structs(model, grads, masks, need_grads=True)
+    with torch.cuda.device(mix.device):
+        _lib.check(_lib.load().svs_unet_train_backward(arr, mix.data_ptr(), grad_mask.data_ptr(), b, ws.data_ptr(),
+                                                       ws.numel(), _lib.stream_ptr(mix.device)),
+                   "svs_unet_train_backward")
+
+
+class _TrainForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mix, model, masks, *params):
+        ctx.model, ctx.masks = model, masks
+        ctx.save_for_backward(mix)
+        return _raw_forward(model, mix, masks)
+
+    @staticmethod
+    def backward(ctx, grad_mask):
+        (mix,) = ctx.saved_tensors
+        model = ctx.model
+        grads = [torch.empty_like(p) for p in param_list(model)]
+        _raw_backward(model, mix, grad_mask.contiguous().float(), ctx.masks, grads)
+        return (None, None, None) + tuple(grads)
+
+
+def train_forward(model, mix, injected_masks=None):
+    """``UNet.forward`` in train mode: returns the mask with an autograd edge to every parameter."""
+    mix = mix.contiguous()
+    _check_inputs(model, mix)
+    masks = dropout_masks(model, mix.shape[0], injected_masks if injected_masks is not None
+                          else getattr(model, "_injected_dropout_masks", None))
+    if not torch.is_grad_enabled():
+        return _raw_forward(model, mix, masks)
+    return _TrainForward.apply(mix, model, masks, *param_list(model))
+
+
+def masked_l1(mask, mix, voc, two_term=True, grad_scale=1.0, want_grad=True):
+    """svs_l1_masked_loss: (loss tensor [3] = total / vocal / accompaniment, dL/dmask or None)."""
+    loss = torch.empty(3, dtype=torch.float32, device=mask.device)
+    grad = torch.empty_like(mask) if want_grad else None
+    with torch.cuda.device(mask.device):
+        _lib.check(_lib.load().svs_l1_masked_loss(mask.data_ptr(), mix.data_ptr(), voc.data_ptr(), mask.numel(),
+                                                  1 if two_term else 0, float(grad_scale), loss.data_ptr(),
+                                                  grad.data_ptr() if grad is not None else None,
+                                                  _lib.stream_ptr(mask.device)), "svs_l1_masked_loss")
+    return loss, grad
+
+
+def train_step(model, mix, voc, two_term: bool = True, loss_scale: float = 1.0, step: bool = True,
+               injected_masks=None):
+    """One fused optimisation step (reference train.py:271-300 without the MR-STFT term).
+
+    Returns the device tensor [total, vocal, accompaniment] of the UNSCALED L1 loss.  Gradients are
+    written into one flat fp32 buffer (``model._flat_grad``, 9,823,313 floats); with an initialised
+    ``torch.distributed`` process group they are averaged across ranks by a single NCCL all-reduce."""
+    mix = mix.contiguous()
+    voc = voc.contiguous()
+    _check_inputs(model, mix)
+    _lib.require_cuda(voc, "voc", torch.float32)
+    masks = dropout_masks(model, mix.shape[0], injected_masks)
+    flat, views = _flat_grads(model)
+    with torch.no_grad():
+        mask = _raw_forward(model, mix, masks)
+        loss, grad_mask = masked_l1(mask, mix, voc, two_term, loss_scale)
+        _raw_backward(model, mix, grad_mask, masks, views)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1:
+                torch.distributed.all_reduce(flat)
+                flat.div_(world)
+        for p, g in zip(param_list(model), views):
+            p.grad = g
+        if step:
+            model.optim.step()
+    return loss
