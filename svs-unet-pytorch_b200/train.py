@@ -1,0 +1,202 @@
+"""Drop-in for reference train.py (same flags, checkpoint dict, CKPT/ and LOG/ conventions) on the
+sm_100a training kernels.
+
+Differences, all outside the kernels' arithmetic and stated here so they are not silent:
+* the loss is ``alpha_L1 * (L1(mask*mix, voc) + L1((1-mask)*mix, clamp(mix-voc, 0)))`` (train.py:275-283,296
+  with crit = nn.L1Loss, reference config.py:33,44).  The MR-STFT term of train.py:287-296 needs
+  ``auraloss`` (not installable here) and is out of the hot-path scope ("next").
+* ``SpectrogramDataset`` keeps every song's spectrogram resident in HBM and cuts the random 128-frame
+  crops on the device (the reference re-reads four .npy files per sample in 8 DataLoader workers,
+  train.py:86-143,182); the phase files are not needed without the MR-STFT term.
+* with WORLD_SIZE > 1 (torchrun) the step is data parallel: one NCCL all-reduce of the flat gradient
+  buffer per step; rank 0 writes checkpoints and logs.  The reference is single device.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import _lib, training
+from .config import INPUT_LEN, SAMPLES_PER_SONG
+from .model import UNet
+
+alpha_L1 = 166.66          # reference train.py:24
+
+
+class SpectrogramDataset:
+    """GPU-resident mirror of reference train.py:65-143: ``<path>/mixture/*_spec.npy`` with a matching
+    ``<path>/vocal/`` file; ``len = n_songs * samples_per_song``; item = random 128-frame crop (shared
+    start for mixture and vocal), DC row dropped, zero padded when the song is shorter."""
+
+    def __init__(self, path, samples_per_song=SAMPLES_PER_SONG, device="cuda", seed=None):
+        self.mixture_path = os.path.join(path, "mixture")
+        self.vocal_path = os.path.join(path, "vocal")
+        self.samples_per_song = samples_per_song
+        if not os.path.exists(self.mixture_path):
+            raise FileNotFoundError(f"mixture folder not found: {self.mixture_path}")
+        names = sorted(f for f in os.listdir(self.mixture_path) if f.endswith("_spec.npy"))
+        self.file_names = [f for f in names if os.path.exists(os.path.join(self.vocal_path, f))]
+        self.device = torch.device(device)
+        self.mix, self.voc = [], []
+        for f in self.file_names:                                    # [T][512] on the device, DC dropped
+            m = np.load(os.path.join(self.mixture_path, f))[1:, :]
+            v = np.load(os.path.join(self.vocal_path, f))[1:, :]
+            self.mix.append(torch.from_numpy(np.ascontiguousarray(m, dtype=np.float32)).to(self.device))
+            self.voc.append(torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(self.device))
+        self.rng = random.Random(seed)
+        print(f"[{os.path.basename(path)}] loaded {len(self.file_names)} songs, {samples_per_song} samples per "
+              f"song per epoch, {len(self)} items.")
+
+    def __len__(self):
+        return len(self.file_names) * self.samples_per_song
+
+    def item(self, idx):
+        s = idx % len(self.file_names)
+        mix, voc = self.mix[s], self.voc[s]
+        cur = mix.shape[1]
+        if cur > INPUT_LEN:
+            start = self.rng.randint(0, cur - INPUT_LEN)              # train.py:116 (shared start)
+            return mix[:, start:start + INPUT_LEN], voc[:, start:start + INPUT_LEN]
+        pad = INPUT_LEN - cur
+        return torch.nn.functional.pad(mix, (0, pad)), torch.nn.functional.pad(voc, (0, pad))
+
+    def batches(self, batch_size, shuffle=True, rank=0, world=1):
+        order = list(range(len(self)))
+        if shuffle:
+            self.rng.shuffle(order)
+        order = order[rank::world]
+        for a in range(0, len(order), batch_size):
+            items = [self.item(i) for i in order[a:a + batch_size]]
+            mix = torch.stack([m for m, _ in items]).unsqueeze(1).contiguous()
+            voc = torch.stack([v for _, v in items]).unsqueeze(1).contiguous()
+            yield mix, voc
+
+    def n_batches(self, batch_size, world=1):
+        per_rank = (len(self) + world - 1) // world
+        return (per_rank + batch_size - 1) // batch_size
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--train_folder", type=str, default="./data/vocals")
+    p.add_argument("--load_path", type=str, default="result.pth")
+    p.add_argument("--label", type=str, required=True)
+    p.add_argument("--epoch", type=int, default=2)
+    p.add_argument("--batch_size", type=int, default=2)
+    p.add_argument("--valid_folder", type=str, default="unet_spectrograms/valid")
+    p.add_argument("--val_interval", type=int, default=20)
+    return p
+
+
+def make_checkpoint(model, epoch, scheduler=None):
+    ckpt = {"epoch": epoch, "model_state_dict": model.state_dict(), "optim": model.optim.state_dict(),
+            "scheduler": scheduler.state_dict() if scheduler is not None else None}
+    for key in model.__dict__:                                       # train.py:377-379
+        if key.startswith("loss_list"):
+            ckpt[key] = getattr(model, key)
+    return ckpt
+
+
+@torch.no_grad()
+def validate(model, dataset, batch_size, rank=0, world=1):
+    model.eval()
+    total, n = 0.0, 0
+    for mix, voc in dataset.batches(batch_size, shuffle=False, rank=rank, world=world):
+        mask = model(mix)
+        loss, _ = training.masked_l1(mask, mix, voc, two_term=True, want_grad=False)
+        total += alpha_L1 * float(loss[0])
+        n += 1
+    return total / max(n, 1)
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if not torch.cuda.is_available():
+        raise _lib.SvsError("training needs a B200: svs-unet-pytorch_b200 has no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=device)
+    print(f"Using device: {device} (rank {rank}/{world})")
+    os.makedirs("CKPT", exist_ok=True)
+    os.makedirs("LOG", exist_ok=True)
+    log_file = f"LOG/log_{args.label}.txt"
+    best_weight = f"CKPT/svs_best_{args.label}.pth"
+    ckpt_weight = f"CKPT/svs_{args.label}.pth"
+
+    train_set = SpectrogramDataset(args.train_folder, device=device, seed=None if world == 1 else 1234 + rank)
+    valid_set = None
+    if os.path.exists(args.valid_folder):
+        vs = SpectrogramDataset(args.valid_folder, device=device)
+        valid_set = vs if len(vs) > 0 else None
+    else:
+        print(f"Warning: validation folder {args.valid_folder} not found, skipping validation.")
+
+    model = UNet().to(device)
+    start_epoch, scheduler = 0, None
+    if os.path.exists(args.load_path):                               # train.py:216-237
+        print(f"Loading checkpoint from {args.load_path}")
+        ckpt = torch.load(args.load_path, map_location=device)
+        model.load_state_dict(ckpt["model_state_dict"])
+        if "optim" in ckpt:
+            model.optim.load_state_dict(ckpt["optim"])
+        start_epoch = ckpt.get("epoch", 0)
+        for key in ckpt:
+            if key.startswith("loss_list"):
+                setattr(model, key, ckpt[key])
+    if world > 1:                                                    # identical replicas
+        for t in list(model.parameters()) + list(model.buffers()):
+            torch.distributed.broadcast(t.data, 0)
+
+    best_val, log_buffer = 100.0, []
+    print(f"Start training for {args.epoch - start_epoch} epochs...")
+    for ep in range(start_epoch, args.epoch):
+        model.train()
+        if ep == 400:                                                # train.py:251-262
+            for group in model.optim.param_groups:
+                group["lr"] = 5e-4
+            if rank == 0:
+                torch.save(make_checkpoint(model, ep + 1), f"CKPT/svs_{args.label}_400.pth")
+            print(f"\n[Info] Epoch {ep}: Learning rate manually changed to 5e-4!\n")
+        loss_sum, n_it = 0.0, 0
+        for mix, voc in train_set.batches(args.batch_size, shuffle=True, rank=rank, world=world):
+            if mix.shape[0] < 2:
+                continue                                             # batch-statistic BatchNorm needs > 1 sample
+            loss = training.train_step(model, mix, voc, two_term=True, loss_scale=alpha_L1)
+            loss_sum += alpha_L1 * float(loss[0])                    # train.py:303 (.item() per step)
+            n_it += 1
+        avg = loss_sum / max(n_it, 1)
+        log_buffer.append(f"{avg}\n")
+        if valid_set is not None and (ep + 1) % args.val_interval == 0:
+            val = validate(model, valid_set, args.batch_size, rank, world)
+            log_buffer.append(f"Val {val}\n")
+            print(f"\n[Epoch {ep + 1}] Train Loss: {avg:.4e} | Val Loss: {val:.4e}")
+            if val < best_val and rank == 0:
+                best_val = val
+                model.save(best_weight)                              # train.py:353-355
+            if rank == 0:
+                with open(log_file, "a") as f:
+                    f.writelines(log_buffer)
+            log_buffer = []
+        else:
+            print(f"Epoch {ep + 1} Avg Loss: {avg:.4e}")
+        if rank == 0:
+            torch.save(make_checkpoint(model, ep + 1, scheduler), ckpt_weight)
+    if log_buffer and rank == 0:
+        with open(log_file, "a") as f:
+            f.writelines(log_buffer)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    print("Finish training!")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,89 @@
+"""GPU: the three drop-in command lines end to end on a tiny synthetic song folder, checked against the
+oracle's restatement of reference data.py / inference.py, plus one epoch of the train.py drop-in."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import stft_oracle as so, unet_oracle  # noqa: E402
+from svs_unet_pytorch_b200 import audio_io, data, inference, model as svs_model, synth, train  # noqa: E402
+
+
+def _make_songs(root, n=2, seconds=13.0):
+    stems = []
+    for i in range(n):
+        mix, voc, _ = synth.synth_song(seconds + i, seed=100 + i)
+        d = os.path.join(root, f"song{i}")
+        os.makedirs(d)
+        audio_io.write_wav_pcm16(os.path.join(d, "mixture.wav"), mix, 8192)
+        audio_io.write_wav_pcm16(os.path.join(d, "vocals.wav"), voc, 8192)
+        stems.append((audio_io.load(os.path.join(d, "mixture.wav"), 8192),
+                      audio_io.load(os.path.join(d, "vocals.wav"), 8192)))
+    return stems
+
+
+def test_to_spec_inference_to_wave(tmp_path):
+    src, spec_dir, pred_dir, wav_dir = (str(tmp_path / n) for n in ("songs", "spec", "pred", "wav"))
+    os.makedirs(src)
+    stems = _make_songs(src)
+    data.main(["--src", src, "--tar", spec_dir, "--direction", "to_spec"])
+    torch.manual_seed(0)
+    net = svs_model.UNet()
+    ckpt = str(tmp_path / "svs_test.pth")
+    torch.save({"epoch": 1, "model_state_dict": net.state_dict(), "optim": net.optim.state_dict(),
+                "scheduler": None}, ckpt)                             # reference train.py:369-374 layout
+    os.environ["SVS_B200_PRECISION"] = "tf32"
+    try:
+        inference.main(["--model_path", ckpt, "--mixture_folder", os.path.join(spec_dir, "mixture"), "--tar", pred_dir,
+                        "--vocal_solo", "1"])
+    finally:
+        del os.environ["SVS_B200_PRECISION"]
+    data.main(["--src", pred_dir, "--phase", spec_dir, "--tar", wav_dir, "--direction", "to_wave"])
+    sd = net.state_dict()
+    for i, (mix, voc) in enumerate(stems):
+        base = f"{i:04d}_song{i}"
+        spec = np.load(os.path.join(spec_dir, "mixture", base + "_spec.npy"))
+        phase = np.load(os.path.join(spec_dir, "mixture", base + "_phase.npy"))
+        vspec = np.load(os.path.join(spec_dir, "vocal", base + "_spec.npy"))
+        rspec, rphase, _ = so.to_spec(mix)
+        rvspec, _, _ = so.to_spec(mix, voc)
+        assert spec.shape == rspec.shape and spec.dtype == np.float32 and spec.flags["F_CONTIGUOUS"]
+        assert phase.dtype == np.complex64 and phase.shape == rphase.shape
+        assert np.abs(spec - rspec).max() <= 1e-4 and np.abs(vspec - rvspec).max() <= 1e-4
+        assert spec.max() == np.float32(1.0)
+        pred = np.load(os.path.join(pred_dir, base + "_spec.npy"))
+        rpred = unet_oracle.separate_spectrogram(sd, rspec, vocal_solo=True)
+        assert pred.shape == rpred.shape and pred.dtype == np.float32 and np.all(pred[0] == 0)
+        assert np.abs(pred - rpred).max() <= 1e-3
+        y, sr = audio_io.read_wav(os.path.join(wav_dir, base + ".wav"))
+        ry = so.to_wave(rpred, rphase)
+        assert sr == 8192 and y.shape == ry.shape
+        assert abs(synth.sdr_db(voc, y) - synth.sdr_db(voc, ry)) <= 0.05
+
+
+def test_train_cli_one_epoch(tmp_path, monkeypatch):
+    src, spec_dir = str(tmp_path / "songs"), str(tmp_path / "spec")
+    os.makedirs(src)
+    _make_songs(src, n=2)
+    data.main(["--src", src, "--tar", spec_dir, "--direction", "to_spec"])
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(train, "SAMPLES_PER_SONG", 4)
+    ds = train.SpectrogramDataset(spec_dir, samples_per_song=4, device="cuda", seed=0)
+    assert len(ds) == 8
+    mix, voc = next(ds.batches(4))
+    assert mix.shape == voc.shape == (4, 1, 512, 128) and mix.is_cuda
+    train.main(["--train_folder", spec_dir, "--valid_folder", spec_dir, "--label", "t", "--epoch", "2",
+                "--batch_size", "4", "--val_interval", "1", "--load_path", "none.pth"])
+    ckpt = torch.load(str(tmp_path / "CKPT" / "svs_t.pth"), map_location="cpu")
+    assert ckpt["epoch"] == 2 and set(ckpt) >= {"model_state_dict", "optim", "scheduler", "loss_list_total"}
+    assert len(ckpt["model_state_dict"]) == 79
+    assert os.path.exists(str(tmp_path / "CKPT" / "svs_best_t.pth"))
+    lines = open(str(tmp_path / "LOG" / "log_t.txt")).read().split("\n")
+    assert any(l.startswith("Val ") for l in lines) and float(lines[0]) > 0      # loss_plot.py format
+    # resume from the checkpoint (train.py:216-237)
+    train.main(["--train_folder", spec_dir, "--valid_folder", "missing", "--label", "t", "--epoch", "3",
+                "--batch_size", "4", "--load_path", str(tmp_path / "CKPT" / "svs_t.pth")])
+    assert torch.load(str(tmp_path / "CKPT" / "svs_t.pth"), map_location="cpu")["epoch"] == 3
