@@ -23,6 +23,7 @@
 #include "tc_ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <type_traits>
 #include <cstdlib>
 #include <mutex>
 
@@ -81,6 +82,14 @@ constexpr size_t tc_smem_bytes() {
 }
 
 
+template <int S, int N, typename F>
+__device__ __forceinline__ void dispatch_stage(int s, F&& f) {
+  if constexpr (S < N) {
+    if (s == S) f(std::integral_constant<int, S>{});
+    else dispatch_stage<S + 1, N>(s, f);
+  }
+}
+
 // Persistent kernel: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is
 // double buffered in TMEM so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
 // tile index -> (z = phase * split_k + split, n tile, m tile) with m fastest (neighbouring CTAs share
@@ -136,8 +145,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
+    {
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int z = tile / per_z, rem = tile - z * per_z;
@@ -154,19 +163,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int s = it % kStages;
           const uint32_t par = (it / kStages) & 1;
           mbar_wait(empty_bar(s), par ^ 1);
-          mbar_expect_tx(full_bar(s), kStageBytes);
           const TcChunk ch = chunks[ci];
           const uint32_t a_dst = smem_base + s * kStageBytes;
-          tma_load_5d(a_dst, &tmap_a, full_bar(s), ch.c_inner, tw * p.bw + ch.dw, ch.ph, th * p.bh + ch.dh,
-                      tb * p.nb);
-          tma_load_2d(a_dst + kABytes, tb_map, full_bar(s), ci * p.block_k, nt * kBlockN);
+          if (elect_one_sync()) {
+            mbar_expect_tx(full_bar(s), kStageBytes);
+            tma_load_5d(a_dst, &tmap_a, full_bar(s), ch.c_inner, tw * p.bw + ch.dw, ch.ph, th * p.bh + ch.dh,
+                        tb * p.nb);
+            tma_load_2d(a_dst + kABytes, tb_map, full_bar(s), ci * p.block_k, nt * kBlockN);
+          }
+          __syncwarp();
         }
       }
     }
     __syncwarp();                               // reconverge before the aligned block barrier below
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: uniform control flow, one elected lane issues tcgen05.mma / commit =====
+    {
       constexpr uint32_t idesc = make_idesc<kTf32, kBlockN>();
       int it = 0, t = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
@@ -184,20 +196,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int s = it % kStages;
           const uint32_t par = (it / kStages) & 1;
           mbar_wait(full_bar(s), par);
-          if (dbg && it == 0) dbg[2] = clock64();
+          if (dbg && it == 0 && lane == 0) dbg[2] = clock64();
           tc_fence_after();
-          const uint32_t a_addr = smem_base + s * kStageBytes;
-          const uint64_t da = make_smem_desc<kSwz>(a_addr);
-          const uint64_t db = make_smem_desc<kSwz>(a_addr + kABytes);
+          // dispatch on the stage index so that descriptors are "uniform base + compile-time constant":
+          // descriptor arithmetic in the vector datapath costs an R2UR chain per MMA (see zc_conv.cu)
+          const uint32_t acc0 = i > 0 ? 1u : 0u;
+          dispatch_stage<0, kStages>(s, [&](auto sc) {
+            constexpr int S = decltype(sc)::value;
+            const uint32_t a_addr = smem_base + S * kStageBytes;
+            const uint64_t da = make_smem_desc<kSwz>(a_addr);
+            const uint64_t db = make_smem_desc<kSwz>(a_addr + kABytes);
+            if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kMmaPerChunk; ++k) {
-            // advance 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma<kTf32>(tmem_d, da + 2u * k, db + 2u * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
+              for (int k = 0; k < kMmaPerChunk; ++k) {
+                // advance 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+                umma<kTf32>(tmem_d, da + 2u * k, db + 2u * k, idesc, k > 0 ? 1u : acc0);
+              }
+              umma_commit(bar_base + 8u * (kStages + S));   // empty_bar(S): frees the stage when the MMAs retire
+            }
+            __syncwarp();
+          });
         }
-        umma_commit(tmem_full_bar(as));         // accumulator complete
-        if (dbg && t == 0) dbg[3] = clock64();
+        if (elect_one_sync()) umma_commit(tmem_full_bar(as));   // accumulator complete
+        __syncwarp();
+        if (dbg && t == 0 && lane == 0) dbg[3] = clock64();
       }
     }
     __syncwarp();

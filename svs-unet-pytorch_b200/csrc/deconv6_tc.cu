@@ -71,7 +71,8 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+    if (elect_one_sync()) {
     mbar_expect_tx(bar_full, kABytes + kWBytes);
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
@@ -79,17 +80,22 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         "l"(reinterpret_cast<uint64_t>(&tmap_a)), "r"(bar_full), "r"(0), "r"(0), "r"(row0), "r"(b)
         : "memory");
     tma_load_2d(smem_base + kABytes, &tmap_w, bar_full, 0, 0);
+    }
+    __syncwarp();
     mbar_wait(bar_full, 0);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc<kTf32, 32>();
     const uint64_t dw = make_smem_desc<kSwz>(smem_base + kABytes);
+    if (elect_one_sync()) {
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      const uint64_t da = make_smem_desc<kSwz>(smem_base + mt * 128 * kSwz);
+      for (int mt = 0; mt < 4; ++mt) {
+        const uint64_t da = make_smem_desc<kSwz>(smem_base + mt * 128 * kSwz);
 #pragma unroll
-      for (int k = 0; k < kKSteps; ++k) umma<kTf32>(tmem_base + mt * 32, da + 2u * k, dw + 2u * k, idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < kKSteps; ++k) umma<kTf32>(tmem_base + mt * 32, da + 2u * k, dw + 2u * k, idesc, k > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_mma);
     }
-    umma_commit(bar_mma);
+    __syncwarp();
   }
   if (warp >= 4) {
     // drain the 4 accumulators into P[tap][pixel]; the MMAs have finished reading the operand slab

@@ -24,6 +24,10 @@ void tc_free_layers(svs_unet_plan* plan);
 size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch);
 int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st);
 int tc_launch_count(const svs_unet_plan* plan, int li, int batch);
+// zc_conv.cu
+int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st);
+void zc_free_layers(svs_unet_plan* plan);
+int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st);
 // deconv6_tc.cu
 int d6_plan(svs_unet_plan* plan, cudaStream_t st);
 void d6_free(svs_unet_plan* plan);
@@ -89,6 +93,11 @@ extern "C" int svs_unet_plan_create(const svs_conv_params layers[12], int precis
   if (precision != SVS_PRECISION_FP32) {
     rc = tc_plan_layers(plan, st);
     if (rc != SVS_OK) { svs_unet_plan_destroy(plan); return rc; }
+    for (int li = 1; li <= 10; ++li) {
+      if (!plan->tc[li].enabled) continue;
+      rc = zc_plan_layer(plan, li, st);
+      if (rc != SVS_OK) { svs_unet_plan_destroy(plan); return rc; }
+    }
     const char* dis = std::getenv("SVS_TC_DISABLE_MASK");
     if (!(dis && ((std::strtoul(dis, nullptr, 0) >> 11) & 1u))) {
       rc = d6_plan(plan, st);
@@ -102,6 +111,7 @@ extern "C" int svs_unet_plan_create(const svs_conv_params layers[12], int precis
 extern "C" int svs_unet_plan_destroy(svs_unet_plan* plan) {
   if (!plan) return SVS_OK;
   tc_free_layers(plan);
+  zc_free_layers(plan);
   d6_free(plan);
   for (int i = 0; i < 12; ++i) {
     if (plan->w_fold[i]) cudaFree(plan->w_fold[i]);
@@ -144,7 +154,8 @@ extern "C" int svs_unet_forward_layers(const svs_unet_plan* plan, const svs_patc
   for (int li = first_layer; li <= last_layer; ++li) {
     int rc;
     if (li == 11 && plan->d6_enabled) rc = d6_launch(plan, ws, in, out, in_frames, batch, flags, st);
-    else if (plan->tc[li].enabled) rc = tc_launch_layer(plan, li, ws, batch, st);
+    else if (plan->tc[li].enabled)
+      rc = plan->zc[li].enabled ? zc_launch_layer(plan, li, ws, batch, st) : tc_launch_layer(plan, li, ws, batch, st);
     else rc = launch_layer_direct(plan, li, ws, in, out, in_frames, batch, flags, st);
     if (rc != SVS_OK) return rc;
   }
@@ -163,6 +174,7 @@ extern "C" int svs_unet_read_activation(const svs_unet_plan* plan, int layer, in
 extern "C" int svs_unet_launch_count(const svs_unet_plan* plan, int batch) {
   if (!plan || batch <= 0) return 0;
   int n = 0;
-  for (int li = 0; li < 12; ++li) n += plan->tc[li].enabled ? tc_launch_count(plan, li, batch) : 1;
+  for (int li = 0; li < 12; ++li)
+    n += (plan->tc[li].enabled && !plan->zc[li].enabled) ? tc_launch_count(plan, li, batch) : 1;
   return n;
 }

@@ -93,6 +93,23 @@ struct TcLayer {
   mutable int tmap_a_batch = -1;
 };
 
+// ---- zero-copy tcgen05 layers (zc_conv.cu) -------------------------------------------------------
+constexpr int kZcMaxTaps = 64, kZcMaxSlabs = 8;
+struct ZcSchedule {
+  int n_slabs, n_taps;
+  int slab_c[kZcMaxSlabs], slab_ph[kZcMaxSlabs];   // TMA coordinates (channel window, row parity) of each halo slab
+  // taps are ordered by slab: (slab, dy, dx) and the mask of non-zero 32-byte k-steps
+  signed char tap_slab[kZcMaxTaps], tap_dy[kZcMaxTaps], tap_dx[kZcMaxTaps], tap_kmask[kZcMaxTaps];
+};
+struct ZcLayer {
+  bool enabled = false;
+  bool resident = false;
+  ZcSchedule sch{};
+  int n_total = 0, row_elems = 0;
+  void* d_weights = nullptr;
+  CUtensorMap tmap_b;
+};
+
 }  // namespace svs
 
 struct svs_unet_plan {
@@ -102,6 +119,7 @@ struct svs_unet_plan {
   float* w_fold[12] = {};            // folded fp32 weights [25][Cin][Cout]
   float* b_fold[12] = {};            // folded fp32 bias [Cout]
   svs::TcLayer tc[12];
+  svs::ZcLayer zc[12];
   // deconv6 as a taps-as-N GEMM + col2im gather (deconv6_tc.cu)
   bool d6_enabled = false;
   void* d6_weights = nullptr;

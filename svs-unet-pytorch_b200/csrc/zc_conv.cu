@@ -1,0 +1,584 @@
+// K3/K4-zc: 5x5 stride-2 convolution and transposed convolution as a ZERO-COPY implicit GEMM on tcgen05.
+//
+// tc_conv_kernel (conv_tc.cu) lets TMA do the im2col: every tap re-loads its own 128-pixel slab, so
+// a conv moves 25/4 x and a phase-merged deconv 9 x its input through L2 -> SMEM, and every mid layer
+// ends up bound by that traffic.  Here each 18 x 10 pixel HALO SLAB (128-byte rows: 64 bf16 / 32 fp32
+// channels, 128B swizzle) of the 16 x 8 pixel tile is landed in shared memory ONCE by one TMA box, and
+// the taps are *descriptor offsets* into it: for a tap shifted by (dy, dx) the A operand starts at row
+// ((dy+1)*10 + (dx+1)) of the slab and its sixteen 8-row core-matrix groups (one image row each) are
+// 10 rows = 1280 B apart — exactly the UMMA descriptor's stride-byte-offset.  The 128B-swizzle XOR is
+// a function of the absolute shared-memory address bits (measured: base_offset = 0 reproduces TMA's
+// placement for any 128-byte-aligned start), so shifted operands read back what TMA wrote.
+//
+//   conv   (stride 2): slabs are parity planes of the rank-5 view (pw*Ct + c, W/2, ph, H/2, B); tap
+//          (kh, kw) = (2 dy + ph + 2, 2 dx + pw + 2).  A 128-byte row may span both column parities
+//          (conv2: Ct = 32) or both halves of a concat buffer; 32-byte k-steps whose weights are all
+//          zero (the other half of the concat buffer, kw = 5) are SKIPPED, not multiplied.
+//   deconv (phase merged): slabs are 64-channel slices of (c, W, 1, H, B); N = 4 phases x Cout and
+//          phase (py, px) uses tap (kh, kw) = (py + 2 - 2 dy, px + 2 - 2 dx) when it exists.
+//   weights: one [N][128 B] K-major chunk per tap; RESIDENT in shared memory for the whole persistent
+//          CTA when they fit (conv2, deconv5), otherwise streamed through a TMA ring.
+#include "unet_internal.cuh"
+#include "tc_ptx.cuh"
+
+#include <cstdlib>
+#include <vector>
+
+namespace svs {
+
+extern long long* g_tc_dbg;
+extern int g_tc_dbg_layer;
+
+constexpr int kZcThreads = 192;
+constexpr int kZcBw = 8, kZcBh = 16;                 // M tile: 16 image rows x 8 pixels
+constexpr int kZcPw = kZcBw + 2, kZcPh = kZcBh + 2;  // halo slab 18 x 10 rows
+constexpr int kZcATx = kZcPw * kZcPh * 128;          // 23,040 bytes landed per slab
+constexpr int kZcASlot = 24576;                      // slot pitch (multiple of 1024)
+
+struct ZcParams {
+  ZcSchedule sch;
+  int row_elems;                 // elements per 128-byte row
+  int ntw, nth, m_tiles, batch;
+  void* out;
+  int out_pitch, out_coff, hout, wout, out_scale;
+  const float* bias;
+  int cout_phase, merged, act;
+  int resident;                  // weights resident in smem
+  long long* dbg;                // profiling: per CTA 64 clock64 stamps
+  int exp_mode;                  // experiments only (wrong numerics): 1 = unshifted start, 2 = + canonical SBO
+};
+
+template <int kBlockN, int kASlots, int kBSlots>
+constexpr size_t zc_smem_bytes() {
+  return static_cast<size_t>(kASlots) * kZcASlot + static_cast<size_t>(kBSlots) * kBlockN * 128 + 1024 + 512 + 2048;
+}
+
+__device__ __forceinline__ float zc_act(float v, int act) {
+  if (act == ACT_LEAKY) return v > 0.0f ? v : 0.2f * v;
+  return fmaxf(v, 0.0f);
+}
+__device__ __forceinline__ void zc_store16(__nv_bfloat16* dst, const float (&f)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void zc_store16(float* dst, const float (&f)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+
+// ---- compile-time tap tables ---------------------------------------------------------------------
+// The MMA issuer must not do per-tap address arithmetic in the vector datapath: tcgen05.mma takes its
+// descriptors from UNIFORM registers and every R2UR hop costs tens of cycles, which at 4 MMAs per tap
+// dominated the issue rate (measured 178 cycles per N=64 MMA against a 48-cycle hardware floor).  With the
+// tap set known at compile time the issue loop unrolls into straight-line code whose descriptors are
+// "slab base + constant".  kmask(s, dy, dx) = active 32-byte k-steps of tap (dy, dx) of slab s, 0 = no tap;
+// the order (s, dy, dx ascending, inactive skipped) is the order zc_plan_layer() packs the weights in.
+struct ZcRuntimeTaps { static constexpr bool kStatic = false; static constexpr int kSlabs = 0;
+  __host__ __device__ static constexpr int kmask(int, int, int) { return 0; } };
+template <int kNSlabs> struct ZcDeconvTaps {      // phase-merged deconv: every slab uses all 9 shifts, full K
+  static constexpr bool kStatic = true; static constexpr int kSlabs = kNSlabs;
+  __host__ __device__ static constexpr int kmask(int, int, int) { return 0xF; } };
+struct ZcConv2Taps {                              // Ct = 32: row = [pw0: d-half | skip | pw1: d-half | skip]; slab = ph
+  static constexpr bool kStatic = true; static constexpr int kSlabs = 2;
+  __host__ __device__ static constexpr int kmask(int s, int dy, int dx) { return (2 * dy + s + 2 > 4) ? 0 : (dx <= 0 ? 0xA : 0x2); } };
+template <int kKMask> struct ZcConvParityTaps {   // slabs (ph, pw) = (s >> 1, s & 1): conv3 (skip half = 0xC), conv4 (0xF)
+  static constexpr bool kStatic = true; static constexpr int kSlabs = 4;
+  __host__ __device__ static constexpr int kmask(int s, int dy, int dx) {
+    return (2 * dy + (s >> 1) + 2 > 4 || 2 * dx + (s & 1) + 2 > 4) ? 0 : kKMask; } };
+
+// kBSlots: ring depth when streaming, number of taps when resident
+template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps>
+__global__ void __launch_bounds__(kZcThreads)
+zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ ZcParams p) {
+  constexpr int kBBytes = kBlockN * 128;
+  constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;
+  constexpr int kTmemCols = 2 * kAccCols;
+  constexpr int kNBar = 2 * kBSlots + 2 * kASlots + 4;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t b_base = smem_base + kASlots * kZcASlot;
+  const size_t bar_off = static_cast<size_t>(kASlots) * kZcASlot + static_cast<size_t>(kBSlots) * kBBytes;
+  const uint32_t bar_base = smem_base + static_cast<uint32_t>(bar_off);
+  auto full_b = [&](int s) { return bar_base + 8u * s; };
+  auto empty_b = [&](int s) { return bar_base + 8u * (kBSlots + s); };
+  auto full_a = [&](int s) { return bar_base + 8u * (2 * kBSlots + s); };
+  auto empty_a = [&](int s) { return bar_base + 8u * (2 * kBSlots + kASlots + s); };
+  auto tmem_full = [&](int s) { return bar_base + 8u * (2 * kBSlots + 2 * kASlots + s); };
+  auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * kBSlots + 2 * kASlots + 2 + s); };
+  static_assert(kNBar * 8 + 8 <= 512, "barrier area");
+  const uint32_t tmem_slot = bar_base + 8u * kNBar;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * kNBar);
+  float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 512);
+  for (int i = threadIdx.x; i < p.cout_phase; i += kZcThreads) sbias[i] = __ldg(&p.bias[i]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = p.dbg ? p.dbg + 64 * blockIdx.x : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  const int total_tiles = p.m_tiles;                  // kBlockN covers all of N
+  const int n_slabs = p.sch.n_slabs, n_taps = p.sch.n_taps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBSlots; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < kASlots; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer: weights (once, or a ring) and halo slabs (a ring running ahead across tiles) =====
+    {
+      if (p.resident) {
+        if (elect_one_sync()) {
+          mbar_expect_tx(full_b(0), static_cast<uint32_t>(n_taps) * kBBytes);
+          for (int t = 0; t < n_taps; ++t)
+            tma_load_2d(b_base + t * kBBytes, &tmap_b, full_b(0), t * p.row_elems, 0);
+        }
+        __syncwarp();
+      }
+      // slab jobs are numbered across tiles; the slab of job j+1 is requested BEFORE the weight chunks
+      // of job j so the halo loads run one slab ahead of the MMAs
+      auto issue_a = [&](int ja, int tile, int s) {
+        const int slot = ja % kASlots;
+        const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, tb = tile / (p.ntw * p.nth);
+        mbar_wait(empty_a(slot), ((ja / kASlots) & 1) ^ 1);
+        if (elect_one_sync()) {
+          mbar_expect_tx(full_a(slot), kZcATx);
+          tma_load_5d(smem_base + slot * kZcASlot, &tmap_a, full_a(slot), p.sch.slab_c[s], tw * kZcBw - 1,
+                      p.sch.slab_ph[s], th * kZcBh - 1, tb);
+        }
+        __syncwarp();
+        if (dbg && ja < 8 && lane == 0) dbg[8 + ja] = clock64();
+      };
+      int ja = 0, jb = 0;
+      if (static_cast<int>(blockIdx.x) < total_tiles) issue_a(0, blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int next_tap = 0;
+        for (int s = 0; s < n_slabs; ++s, ++ja) {
+          if (s + 1 < n_slabs) issue_a(ja + 1, tile, s + 1);
+          else if (tile + static_cast<int>(gridDim.x) < total_tiles) issue_a(ja + 1, tile + gridDim.x, 0);
+          if (!p.resident) {
+            for (; next_tap < n_taps && p.sch.tap_slab[next_tap] == s; ++next_tap, ++jb) {
+              const int bs = jb % kBSlots;
+              mbar_wait(empty_b(bs), ((jb / kBSlots) & 1) ^ 1);
+              if (elect_one_sync()) {
+                mbar_expect_tx(full_b(bs), kBBytes);
+                tma_load_2d(b_base + bs * kBBytes, &tmap_b, full_b(bs), next_tap * p.row_elems, 0);
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    {
+      constexpr uint32_t idesc = make_idesc<kTf32, kBlockN>();
+      int ja = 0, jb = 0, t = 0;
+      if (p.resident) { mbar_wait(full_b(0), 0); tc_fence_after(); }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int as = t & 1;
+        mbar_wait(tmem_empty(as), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kAccCols;
+        if constexpr (Taps::kStatic) {
+          // ---- straight-line issue: slabs, shifts and k-steps unrolled at compile time ----
+          bool first_mma = true;
+          int tap_c = 0;                                // compile-time after unrolling
+#pragma unroll
+          for (int s = 0; s < Taps::kSlabs; ++s, ++ja) {
+            const int slot = ja % kASlots;
+            mbar_wait(full_a(slot), (ja / kASlots) & 1);
+            if (dbg && ja < 8 && lane == 0) dbg[16 + ja] = clock64();
+            tc_fence_after();
+            const uint32_t a_base = smem_base + slot * kZcASlot;
+            const uint64_t da0 = static_cast<uint64_t>((a_base & 0x3FFFF) >> 4) | (1ull << 16) |
+                                 (static_cast<uint64_t>((kZcPw * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx) {
+                const int kmask = Taps::kmask(s, dy, dx);
+                if (kmask == 0) continue;
+                uint32_t b_addr;
+                int bs = 0;
+                if (p.resident) {
+                  b_addr = b_base + tap_c * kBBytes;
+                } else {
+                  bs = jb % kBSlots;
+                  mbar_wait(full_b(bs), (jb / kBSlots) & 1);
+                  tc_fence_after();
+                  b_addr = b_base + bs * kBBytes;
+                }
+                const uint64_t db = make_smem_desc<128>(b_addr);
+                const uint32_t a_off16 = static_cast<uint32_t>(((dy + 1) * kZcPw + (dx + 1)) * 128) >> 4;
+                if (elect_one_sync()) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    if (kmask & (1 << k)) {
+                      umma<kTf32>(tmem_d, da0 + a_off16 + 2u * k, db + 2u * k, idesc, first_mma ? 0u : 1u);
+                      first_mma = false;
+                    }
+                  }
+                  if (!p.resident) umma_commit(empty_b(bs));
+                }
+                __syncwarp();
+                first_mma = false;
+                if (!p.resident) ++jb;
+                ++tap_c;
+              }
+            }
+            if (elect_one_sync()) umma_commit(empty_a(slot));
+            __syncwarp();
+          }
+        } else {
+        uint32_t first = 0;                             // accumulate flag: 0 for the tile's first MMA
+        int tap = 0;
+        for (int s = 0; s < n_slabs; ++s, ++ja) {
+          const int slot = ja % kASlots;
+          mbar_wait(full_a(slot), (ja / kASlots) & 1);
+          if (dbg && ja < 8 && lane == 0) dbg[16 + ja] = clock64();
+          tc_fence_after();
+          const uint32_t a_base = smem_base + slot * kZcASlot;
+          for (; tap < n_taps && p.sch.tap_slab[tap] == s; ++tap) {
+            uint32_t b_addr;
+            int bs = 0;
+            if (p.resident) {
+              b_addr = b_base + tap * kBBytes;
+            } else {
+              bs = jb % kBSlots;
+              mbar_wait(full_b(bs), (jb / kBSlots) & 1);
+              tc_fence_after();
+              b_addr = b_base + bs * kBBytes;
+            }
+            uint32_t a_addr = a_base + ((p.sch.tap_dy[tap] + 1) * kZcPw + (p.sch.tap_dx[tap] + 1)) * 128;
+            uint32_t sbo = kZcPw * 128;
+            if (p.exp_mode >= 1) a_addr = a_base;
+            if (p.exp_mode >= 2) sbo = 1024;
+            // SW128 K-major; 8-row groups (one image row) are 10 slab rows = 1280 B apart; base_offset 0
+            const uint64_t da = static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4) | (1ull << 16) |
+                                (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            const uint64_t db = make_smem_desc<128>(b_addr);
+            const int kmask = p.sch.tap_kmask[tap];
+            const int k_lo = __ffs(kmask) - 1;             // first active k-step of this tap
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (kmask & (1 << k)) umma<kTf32>(tmem_d, da + 2u * k, db + 2u * k, idesc, (first != 0u || k != k_lo) ? 1u : 0u);
+              }
+              if (!p.resident) umma_commit(empty_b(bs));
+            }
+            __syncwarp();
+            first = 1u;
+            if (!p.resident) ++jb;
+          }
+          if (elect_one_sync()) umma_commit(empty_a(slot));
+          __syncwarp();
+        }
+        }
+        if (elect_one_sync()) umma_commit(tmem_full(as));
+        __syncwarp();
+        if (dbg && t < 8 && lane == 0) dbg[24 + t] = clock64();
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int r = 32 * q + lane;
+    const int ix = r & 7, iy = r >> 3;
+    int t = 0;
+    OutT* const out_base = reinterpret_cast<OutT*>(p.out);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, b = tile / (p.ntw * p.nth);
+      const int gx = tw * kZcBw + ix, gy = th * kZcBh + iy;
+      const int as = t & 1;
+      mbar_wait(tmem_full(as), (t >> 1) & 1);
+      if (dbg && t < 8 && threadIdx.x == 64) dbg[32 + t] = clock64();
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccCols;
+      constexpr int kStep = kBlockN >= 32 ? 32 : 16;
+#pragma unroll 2
+      for (int c = 0; c < kBlockN; c += kStep) {
+        uint32_t v[kStep];
+        tmem_ld16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        if constexpr (kStep == 32) tmem_ld16(taddr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < kStep; h += 16) {
+          int ch = c + h, py = 0, px = 0;
+          if (p.merged) {
+            const int ph = ch / p.cout_phase;
+            ch -= ph * p.cout_phase;
+            py = ph >> 1; px = ph & 1;
+          }
+          const int oy = gy * p.out_scale + py, ox = gx * p.out_scale + px;
+          OutT* dst = out_base + ((static_cast<size_t>(b) * p.hout + oy) * p.wout + ox) * p.out_pitch + p.out_coff + ch;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(&sbias[ch + i]);
+            f[i] = zc_act(__uint_as_float(v[h + i]) + bv.x, p.act);
+            f[i + 1] = zc_act(__uint_as_float(v[h + i + 1]) + bv.y, p.act);
+            f[i + 2] = zc_act(__uint_as_float(v[h + i + 2]) + bv.z, p.act);
+            f[i + 3] = zc_act(__uint_as_float(v[h + i + 3]) + bv.w, p.act);
+          }
+          zc_store16(dst, f);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty(as));
+      if (dbg && t < 8 && threadIdx.x == 64) dbg[40 + t] = clock64();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights: B[n][tap * row_elems + e] for the slab rows described by the schedule
+struct ZcPackArgs {
+  ZcSchedule sch;
+  int row_elems, ct, in_coff, cin, cout, transposed, n_total;
+};
+
+template <typename E>
+__global__ void zc_pack_weights_kernel(const float* __restrict__ w_fold /*[25][cin][cout]*/, ZcPackArgs a,
+                                       E* __restrict__ out) {
+  const int k_total = a.sch.n_taps * a.row_elems;
+  const size_t total = static_cast<size_t>(a.n_total) * k_total;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / k_total);
+    const int k = static_cast<int>(i % k_total);
+    const int tap = k / a.row_elems, e = k % a.row_elems;
+    const int s = a.sch.tap_slab[tap], dy = a.sch.tap_dy[tap], dx = a.sch.tap_dx[tap];
+    const int abs_c = a.sch.slab_c[s] + e;
+    int kh, kw, ci, co;
+    if (!a.transposed) {
+      const int pw = abs_c / a.ct;
+      ci = abs_c % a.ct - a.in_coff;
+      kh = 2 * dy + a.sch.slab_ph[s] + 2;
+      kw = 2 * dx + pw + 2;
+      co = n;
+    } else {
+      const int ph = n / a.cout;
+      co = n % a.cout;
+      ci = abs_c - a.in_coff;
+      kh = (ph >> 1) + 2 - 2 * dy;
+      kw = (ph & 1) + 2 - 2 * dx;
+    }
+    float v = 0.0f;
+    if (kh >= 0 && kh <= 4 && kw >= 0 && kw <= 4 && ci >= 0 && ci < a.cin)
+      v = w_fold[(static_cast<size_t>(kh * 5 + kw) * a.cin + ci) * a.cout + co];
+    if constexpr (sizeof(E) == 2) out[i] = __float2bfloat16_rn(v);
+    else out[i] = v;
+  }
+}
+
+// host: is k-step `k` of tap (slab s, dy, dx) non-zero for any output column?
+static bool kstep_active(const ZcSchedule& sch, const LayerGeom& g, int ct, int row_elems, int s, int dy, int dx, int k) {
+  const int kel = row_elems / 4;
+  for (int e = k * kel; e < (k + 1) * kel; ++e) {
+    const int abs_c = sch.slab_c[s] + e;
+    if (!g.transposed) {
+      const int pw = abs_c / ct, ci = abs_c % ct - g.in_coff;
+      const int kh = 2 * dy + sch.slab_ph[s] + 2, kw = 2 * dx + pw + 2;
+      if (kh >= 0 && kh <= 4 && kw >= 0 && kw <= 4 && ci >= 0 && ci < g.cin) return true;
+    } else {
+      const int ci = abs_c - g.in_coff;
+      if (ci < 0 || ci >= g.cin) continue;
+      for (int ph = 0; ph < 4; ++ph) {
+        const int kh = (ph >> 1) + 2 - 2 * dy, kw = (ph & 1) + 2 - 2 * dx;
+        if (kh >= 0 && kh <= 4 && kw >= 0 && kw <= 4) return true;
+      }
+    }
+  }
+  return false;
+}
+
+int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
+  static const int mode = [] { const char* e = std::getenv("SVS_ZC_DISABLE"); return e ? std::atoi(e) : 0; }();
+  const LayerGeom& g = kLayers[li];
+  ZcLayer& z = plan->zc[li];
+  z.enabled = false;
+  if (mode == 1 || ((mode >> 4) >> li) & 1) return SVS_OK;
+  const bool tf32 = plan->precision == SVS_PRECISION_TF32;
+  const int es = plan->elem_size;
+  const int gh = g.transposed ? g.hin : g.hout, gw = g.transposed ? g.win : g.wout;
+  if (gh % kZcBh != 0 || gw % kZcBw != 0) return SVS_OK;
+  const int n_total = g.transposed ? 4 * g.cout : g.cout;
+  if (n_total != 32 && n_total != 64 && n_total != 128 && n_total != 256) return SVS_OK;
+  const int row = 128 / es;
+  const int ct = kBufGeom[g.in_buf].c;
+  ZcSchedule sch{};
+  auto add_slab = [&](int c, int ph) { sch.slab_c[sch.n_slabs] = c; sch.slab_ph[sch.n_slabs] = ph; return sch.n_slabs++; };
+  if (!g.transposed) {
+    // distinct 128-byte row windows of the parity-merged dim (2*Ct elements) that touch the input channels
+    std::vector<int> windows;
+    for (int pw = 0; pw < 2; ++pw)
+      for (int c = 0; c < g.cin; ++c) {
+        const int w0 = (pw * ct + g.in_coff + c) / row * row;
+        bool seen = false;
+        for (int v : windows) seen |= (v == w0);
+        if (!seen) windows.push_back(w0);
+      }
+    if (static_cast<int>(windows.size()) * 2 > kZcMaxSlabs) return SVS_OK;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int w0 : windows) add_slab(w0, ph);
+  } else {
+    if (g.cin % row != 0 || g.in_coff % row != 0 || g.cin / row > kZcMaxSlabs) return SVS_OK;
+    for (int j = 0; j < g.cin / row; ++j) add_slab(g.in_coff + j * row, 0);
+  }
+  for (int s = 0; s < sch.n_slabs; ++s)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        int kmask = 0;
+        for (int k = 0; k < 4; ++k) kmask |= kstep_active(sch, g, ct, row, s, dy, dx, k) ? (1 << k) : 0;
+        if (!kmask) continue;
+        if (sch.n_taps >= kZcMaxTaps) return SVS_OK;
+        sch.tap_slab[sch.n_taps] = static_cast<signed char>(s);
+        sch.tap_dy[sch.n_taps] = static_cast<signed char>(dy);
+        sch.tap_dx[sch.n_taps] = static_cast<signed char>(dx);
+        sch.tap_kmask[sch.n_taps] = static_cast<signed char>(kmask);
+        ++sch.n_taps;
+      }
+  z.sch = sch;
+  z.n_total = n_total;
+  z.row_elems = row;
+  // resident weights when all tap chunks fit beside a 4-slab ring
+  const size_t w_bytes = static_cast<size_t>(sch.n_taps) * n_total * 128;
+  z.resident = w_bytes <= 80 * 1024 && (sch.n_taps == 9 || sch.n_taps == 15);
+  SVS_CUDA_TRY(cudaMalloc(&z.d_weights, w_bytes));
+  ZcPackArgs a{};
+  a.sch = sch; a.row_elems = row; a.ct = ct; a.in_coff = g.in_coff; a.cin = g.cin; a.cout = g.cout;
+  a.transposed = g.transposed ? 1 : 0; a.n_total = n_total;
+  const size_t total = static_cast<size_t>(n_total) * sch.n_taps * row;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256 > 2368 ? 2368 : (total + 255) / 256);
+  if (tf32) zc_pack_weights_kernel<float><<<blocks, 256, 0, st>>>(plan->w_fold[li], a, static_cast<float*>(z.d_weights));
+  else zc_pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(plan->w_fold[li], a, static_cast<__nv_bfloat16*>(z.d_weights));
+  SVS_CHECK_LAUNCH("zc_pack_weights_kernel");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(sch.n_taps) * row, static_cast<cuuint64_t>(n_total)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(sch.n_taps) * 128};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(row), static_cast<cuuint32_t>(n_total)};
+  int rc = encode_tensor_map(&z.tmap_b, tf32, 2, z.d_weights, dims, strides, box, 128);
+  if (rc != SVS_OK) return rc;
+  z.enabled = true;
+  return SVS_OK;
+}
+
+void zc_free_layers(svs_unet_plan* plan) {
+  for (int li = 0; li < 12; ++li) {
+    if (plan->zc[li].d_weights) cudaFree(plan->zc[li].d_weights);
+    plan->zc[li].d_weights = nullptr;
+    plan->zc[li].enabled = false;
+  }
+}
+
+template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps>
+static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcParams& p, cudaStream_t st) {
+  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps>;
+  constexpr size_t smem = zc_smem_bytes<kBlockN, kASlots, kBSlots>();
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  if (per_sm > 512 / (2 * kAccCols)) per_sm = 512 / (2 * kAccCols);
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > p.m_tiles) grid = p.m_tiles;
+  kern<<<grid, kZcThreads, smem, st>>>(ta, tb, p);
+  SVS_CHECK_LAUNCH("zc_conv_kernel");
+  return SVS_OK;
+}
+
+int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st) {
+  const ZcLayer& z = plan->zc[li];
+  const LayerGeom& g = kLayers[li];
+  const bool tf32 = plan->precision == SVS_PRECISION_TF32;
+  const int es = plan->elem_size;
+  CUtensorMap ta;
+  {
+    const cuuint64_t ct = kBufGeom[g.in_buf].c, H = g.hin, W = g.win;
+    cuuint64_t dims[5], strides[4];
+    if (!g.transposed) {
+      dims[0] = 2 * ct; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = batch;
+      strides[0] = 2 * ct * es; strides[1] = W * ct * es; strides[2] = 2 * W * ct * es; strides[3] = H * W * ct * es;
+    } else {
+      dims[0] = ct; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = batch;
+      strides[0] = ct * es; strides[1] = W * ct * es; strides[2] = W * ct * es; strides[3] = H * W * ct * es;
+    }
+    const cuuint32_t box[5] = {static_cast<cuuint32_t>(z.row_elems), kZcPw, 1, kZcPh, 1};
+    int rc = encode_tensor_map(&ta, tf32, 5, ws.buf[g.in_buf], dims, strides, box, 128);
+    if (rc != SVS_OK) return rc;
+  }
+  ZcParams p{};
+  p.sch = z.sch;
+  p.row_elems = z.row_elems;
+  const int gh = g.transposed ? g.hin : g.hout, gw = g.transposed ? g.win : g.wout;
+  p.ntw = gw / kZcBw; p.nth = gh / kZcBh;
+  p.m_tiles = p.ntw * p.nth * batch;
+  p.batch = batch;
+  p.out = ws.buf[g.out_buf];
+  p.out_pitch = kBufGeom[g.out_buf].c; p.out_coff = g.out_coff;
+  p.hout = g.hout; p.wout = g.wout;
+  p.out_scale = g.transposed ? 2 : 1;
+  p.bias = plan->b_fold[li];
+  p.cout_phase = g.cout;
+  p.merged = g.transposed ? 1 : 0;
+  p.act = g.act;
+  p.resident = z.resident ? 1 : 0;
+  p.dbg = (g_tc_dbg_layer == li) ? g_tc_dbg : nullptr;
+  { const char* e = std::getenv("SVS_ZC_EXP"); p.exp_mode = e ? std::atoi(e) : 0; }
+  const int n = z.n_total;
+  // bf16 layers of the reference network get compile-time tap tables; anything else (TF32 rows are 32
+  // channels wide, so the slab/tap sets differ) runs the same kernel with the runtime schedule
+#define SVS_ZC_STATIC(LI, N, AS, BS, RES, TAPS)                                                     \
+  if (!tf32 && li == LI && n == N && z.resident == RES && z.sch.n_slabs == TAPS::kSlabs)              \
+    return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);
+  SVS_ZC_STATIC(1, 32, 4, 15, true, ZcConv2Taps)
+  SVS_ZC_STATIC(2, 64, 5, 8, false, ZcConvParityTaps<0xC>)
+  SVS_ZC_STATIC(3, 128, 5, 6, false, ZcConvParityTaps<0xF>)
+  SVS_ZC_STATIC(8, 256, 3, 4, false, ZcDeconvTaps<4>)
+  SVS_ZC_STATIC(9, 128, 5, 6, false, ZcDeconvTaps<2>)
+  SVS_ZC_STATIC(10, 64, 4, 9, true, ZcDeconvTaps<1>)
+#undef SVS_ZC_STATIC
+#define SVS_ZC_CASE(N, AS, BS, RES)                                                               \
+  if (n == N && z.resident == RES && (!RES || z.sch.n_taps == BS))                                 \
+    return tf32 ? zc_launch_t<float, true, N, AS, BS, ZcRuntimeTaps>(ta, z.tmap_b, p, st)          \
+                : zc_launch_t<__nv_bfloat16, false, N, AS, BS, ZcRuntimeTaps>(ta, z.tmap_b, p, st);
+  SVS_ZC_CASE(256, 3, 4, false)
+  SVS_ZC_CASE(128, 5, 6, false)
+  SVS_ZC_CASE(64, 5, 8, false)
+  SVS_ZC_CASE(32, 5, 8, false)
+  SVS_ZC_CASE(64, 4, 9, true)      // deconv5: 9 x 8 KB resident
+  SVS_ZC_CASE(32, 4, 15, true)     // conv2: 15 x 4 KB resident
+#undef SVS_ZC_CASE
+  return fail(SVS_ERR_NOT_IMPLEMENTED, "zc_launch_layer: no instantiation for N=" + std::to_string(n));
+}
+
+}  // namespace svs
