@@ -282,6 +282,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               f[i + 2] = tc_act(__uint_as_float(v[h + i + 2]) + bv.z, p.act);
               f[i + 3] = tc_act(__uint_as_float(v[h + i + 3]) + bv.w, p.act);
             }
+            if constexpr (kTf32) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = round_tf32(f[i]);
+            }
             if (valid) store16(dst, f);
           }
         }
@@ -355,7 +359,7 @@ splitk_finish_kernel(const TcParams p) {
     u.y = *reinterpret_cast<uint32_t*>(&c);
     *reinterpret_cast<uint2*>(dst) = u;
   } else {
-    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dst) = make_float4(round_tf32(o[0]), round_tf32(o[1]), round_tf32(o[2]), round_tf32(o[3]));
   }
 }
 
@@ -373,7 +377,7 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w_fold, int cin
     const int2 src = chunk_src[k / bk];
     const float v = w_fold[(static_cast<size_t>(src.x) * cin + src.y + (k % bk)) * cout + n];
     if constexpr (sizeof(E) == 2) out[i] = __float2bfloat16_rn(v);
-    else out[i] = v;
+    else out[i] = round_tf32(v);
   }
 }
 
@@ -398,7 +402,7 @@ __global__ void tc_pack_weights_merged_kernel(const float* __restrict__ w_fold, 
     if (kh >= 0 && kh <= 4 && kw >= 0 && kw <= 4)
       v = w_fold[(static_cast<size_t>(kh * 5 + kw) * cin + src.y + (k % bk)) * cout + co];
     if constexpr (sizeof(E) == 2) out[i] = __float2bfloat16_rn(v);
-    else out[i] = v;
+    else out[i] = round_tf32(v);
   }
 }
 
@@ -423,7 +427,8 @@ int encode_tensor_map(CUtensorMap* map, bool tf32, int rank, void* base, const c
   if (!fn) return fail(SVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+                                : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base,
                   dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -73,15 +73,31 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   if (warp == 0) {
     if (elect_one_sync()) {
-    mbar_expect_tx(bar_full, kABytes + kWBytes);
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_base),
-        "l"(reinterpret_cast<uint64_t>(&tmap_a)), "r"(bar_full), "r"(0), "r"(0), "r"(row0), "r"(b)
-        : "memory");
-    tma_load_2d(smem_base + kABytes, &tmap_w, bar_full, 0, 0);
+      mbar_expect_tx(bar_full, kABytes + kWBytes);
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+          " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_base),
+          "l"(reinterpret_cast<uint64_t>(&tmap_a)), "r"(bar_full), "r"(0), "r"(0), "r"(row0), "r"(b)
+          : "memory");
+      tma_load_2d(smem_base + kABytes, &tmap_w, bar_full, 0, 0);
     }
     __syncwarp();
+  }
+  // ---- prefetch the mixture values this thread will need in the gather (independent of the GEMM), so
+  //      their DRAM latency hides behind TMA + MMA + drain instead of serialising inside the gather loop
+  constexpr int kOutPerThread = 2 * kD6Interior * 128 / kD6Threads;     // 6
+  const int nf = in_frames ? in_frames[b] : SVS_PATCH_FRAMES;
+  const float* mix_b = mix + (mix_off ? mix_off[b] : b * mix_sb);
+  float mixv[kOutPerThread];
+#pragma unroll
+  for (int j = 0; j < kOutPerThread; ++j) {
+    const int o = threadIdx.x + j * kD6Threads;
+    const int ox = o & 127, oyl = o >> 7;
+    const int m = row0 + 1 + (oyl >> 1);
+    const int oy = 2 * m + (oyl & 1);
+    mixv[j] = ((flags & SVS_FLAG_APPLY_MASK) && m < 256 && ox < nf) ? __ldg(mix_b + oy * mix_sf + ox * mix_st) : 1.0f;
+  }
+  if (warp == 0) {
     mbar_wait(bar_full, 0);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc<kTf32, 32>();
@@ -120,11 +136,11 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
 
   // ---- col2im gather + sigmoid + mask: 12 output rows x 128 frames ----
-  const int nf = in_frames ? in_frames[b] : SVS_PATCH_FRAMES;
   const float bs = __ldg(bias);
-  const float* mix_b = mix + (mix_off ? mix_off[b] : b * mix_sb);
   float* out_b = out + (out_off ? out_off[b] : b * out_sb);
-  for (int o = threadIdx.x; o < 2 * kD6Interior * 128; o += kD6Threads) {
+#pragma unroll
+  for (int j = 0; j < kOutPerThread; ++j) {
+    const int o = threadIdx.x + j * kD6Threads;
     const int ox = o & 127, oyl = o >> 7;
     const int mr = 1 + (oyl >> 1);                                     // slab row of the input pixel
     const int m = row0 + mr;                                           // global input row
@@ -148,8 +164,7 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     float mval = 1.0f / (1.0f + __expf(-acc));                         // torch.sigmoid, model.py:200
     if (flags & SVS_FLAG_INVERT) mval = 1.0f - mval;                   // inference.py:102
     const int oy = 2 * m + py;
-    if (flags & SVS_FLAG_APPLY_MASK) mval *= __ldg(mix_b + oy * mix_sf + ox * mix_st);   // inference.py:107
-    out_b[oy * out_sf + ox * out_st] = mval;
+    out_b[oy * out_sf + ox * out_st] = mval * mixv[j];                 // inference.py:107 (mixv = 1 without APPLY_MASK)
   }
   __syncthreads();
   if (warp == 1) {
@@ -166,7 +181,7 @@ __global__ void d6_pack_weights_kernel(const float* __restrict__ w_fold /*[25][3
   if (i >= 32 * 32) return;
   const int tap = i >> 5;
   const float v = tap < kD6Taps ? w_fold[i] : 0.0f;
-  if (tf32) static_cast<float*>(out)[i] = v;
+  if (tf32) static_cast<float*>(out)[i] = round_tf32(v);
   else static_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
 }
 

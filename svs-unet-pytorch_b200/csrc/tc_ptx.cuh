@@ -54,6 +54,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// round-to-nearest TF32 (the tensor core truncates fp32 operands; rounding where values are produced keeps
+// the TF32 path unbiased)
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 // true in exactly one (the same) lane of a converged warp; keeps the surrounding code warp-uniform so
 // descriptors stay in uniform registers and tcgen05.mma issues back to back
 __device__ __forceinline__ bool elect_one_sync() {

@@ -120,6 +120,10 @@ struct svs_unet_plan {
   float* b_fold[12] = {};            // folded fp32 bias [Cout]
   svs::TcLayer tc[12];
   svs::ZcLayer zc[12];
+  // conv1 as a thread-built im2col GEMM (conv1_tc.cu)
+  bool c1_enabled = false;
+  void* c1_weights = nullptr;
+  CUtensorMap c1_tmap_w;
   // deconv6 as a taps-as-N GEMM + col2im gather (deconv6_tc.cu)
   bool d6_enabled = false;
   void* d6_weights = nullptr;

@@ -67,9 +67,10 @@ __device__ __forceinline__ void zc_store16(__nv_bfloat16* dst, const float (&f)[
   reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
   reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
-__device__ __forceinline__ void zc_store16(float* dst, const float (&f)[16]) {
+__device__ __forceinline__ void zc_store16(float* dst, const float (&f)[16]) {   // fp32 activations feed kind::tf32
 #pragma unroll
-  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  for (int i = 0; i < 4; ++i)
+    reinterpret_cast<float4*>(dst)[i] = make_float4(round_tf32(f[4 * i]), round_tf32(f[4 * i + 1]), round_tf32(f[4 * i + 2]), round_tf32(f[4 * i + 3]));
 }
 
 // ---- compile-time tap tables ---------------------------------------------------------------------
@@ -395,7 +396,7 @@ __global__ void zc_pack_weights_kernel(const float* __restrict__ w_fold /*[25][c
     if (kh >= 0 && kh <= 4 && kw >= 0 && kw <= 4 && ci >= 0 && ci < a.cin)
       v = w_fold[(static_cast<size_t>(kh * 5 + kw) * a.cin + ci) * a.cout + co];
     if constexpr (sizeof(E) == 2) out[i] = __float2bfloat16_rn(v);
-    else out[i] = v;
+    else out[i] = round_tf32(v);
   }
 }
 
