@@ -56,10 +56,13 @@ int get_spectral_tables(SpectralTables* out) {
       wsq[m] = w * w;
     }
     // librosa window_sumsquare accumulates float64 w^2 into a float32 buffer, earlier frame first
-    for (int r = 0; r < 768; ++r) env_single[r] = static_cast<float>(wsq[r]);
+    // the kernel multiplies by the RECIPROCAL of librosa's float32 envelope (division only where
+    // env > tiny(float32), else the sample is left as is -> reciprocal 1)
+    auto recip = [](float env) { return env > 1.17549435e-38f ? 1.0f / env : 1.0f; };
+    for (int r = 0; r < 768; ++r) env_single[r] = recip(static_cast<float>(wsq[r]));
     for (int r = 0; r < 256; ++r) {
       const float first = static_cast<float>(wsq[r + 768]);
-      env_both[r] = static_cast<float>(static_cast<double>(first) + wsq[r]);
+      env_both[r] = recip(static_cast<float>(static_cast<double>(first) + wsq[r]));
     }
     DeviceTables t;
     SVS_CUDA_TRY(cudaMalloc(&t.tw, sizeof(float2) * 1024));

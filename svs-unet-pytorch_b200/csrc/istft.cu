@@ -8,21 +8,23 @@
 //
 // With padded position P = p + 512:  frame t covers P in [768 t, 768 t + 1024).  Segment t =
 // [768 t, 768 t + 768) receives frame t (offset r = P - 768 t) and, for r < 256, frame t-1
-// (offset r + 768).  A CTA owns kSeg consecutive segments of one song and transforms kSeg + 1
-// frames (the first one only for its tail), i.e. 1/kSeg redundant transforms and no inter-CTA
-// dependency.
+// (offset r + 768).  A 64-thread group owns 16 consecutive segments of one song and transforms 17
+// frames (the first one only for its tail), i.e. 1/16 redundant transforms and no dependency
+// between groups or CTAs.
 #include "svs_common.cuh"
 #include "fft512.cuh"
 
 namespace svs {
 
 constexpr int kIstftThreads = 256;
-constexpr int kIstftFrames = 16;                 // frames transformed per CTA (4 rounds of 4 groups)
-constexpr int kIstftSeg = kIstftFrames - 1;      // output segments per CTA
-constexpr int kFramePitch = 1024;
-constexpr size_t kIstftSmemBytes =
-    sizeof(float) * (kIstftFrames * kFramePitch + 4 * kFftGroupFloats);
+constexpr int kIstftRun = 16;                    // consecutive hop segments owned by one 64-thread group
+constexpr int kIstftGroupFloats = kFftGroupFloats + 1024 + 256;   // FFT scratch + windowed frame + previous tail
+constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats;
 
+// One 64-thread group walks kIstftRun + 1 consecutive frames of one song: frame t-1's last 256 windowed
+// samples (its "tail") stay in shared memory and are added to the first 256 samples of frame t when the
+// group emits hop segment t.  The first frame of a run is transformed only for its tail (1/16 redundant
+// transforms), so groups and CTAs never depend on each other and every output sample is written once.
 __global__ void __launch_bounds__(kIstftThreads)
 istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase,
                  const int64_t* __restrict__ frame_off, const int64_t* __restrict__ wave_off,
@@ -30,19 +32,18 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
                  const float2* __restrict__ tw1024, const float* __restrict__ hann,
                  const float* __restrict__ env_both, const float* __restrict__ env_single) {
   extern __shared__ float smem[];
-  float* frames = smem;                                     // [kIstftFrames][1024] windowed frames
-  float* scratch_all = smem + kIstftFrames * kFramePitch;
-
   const int song = blockIdx.y;
   const int64_t f0 = frame_off[song];
   const int n_frames = static_cast<int>(frame_off[song + 1] - f0);
-  const int seg_begin = blockIdx.x * kIstftSeg;             // first segment (= frame index) of the CTA
-  if (seg_begin >= n_frames) return;
   const int group = threadIdx.x >> 6;
   const int j = threadIdx.x & 63;
-  float* scratch = scratch_all + group * kFftGroupFloats;
+  const int seg_begin = (blockIdx.x * 4 + group) * kIstftRun;   // first segment (= frame index) of this group
+  if (seg_begin >= n_frames) return;                            // whole group leaves (barriers are per group)
+  float* scratch = smem + group * kIstftGroupFloats;
   float* xre = scratch;
   float* xim = scratch + kFftScratchFloats;
+  float* fr = scratch + kFftGroupFloats;                        // [1024] windowed frame
+  float* tail = fr + 1024;                                      // [256]  frame t-1, samples 768..1023
   const int bar = 1 + group;
 
   FftTwiddles tw;
@@ -51,12 +52,16 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
 #pragma unroll
   for (int q = 0; q < 4; ++q) twp[q] = __ldg(&tw1024[j + 64 * q]);
 
-  // ---- transform frames seg_begin-1 .. seg_begin+kIstftSeg-1 into `frames` ----
-  for (int slot = group; slot < kIstftFrames; slot += 4) {
+  const int64_t w0 = wave_off[song];
+  const int out_len = SVS_HOP * (n_frames - 1);                 // librosa: hop * (T - 1) after trimming
+  float peak = 0.0f;
+
+  for (int slot = 0; slot <= kIstftRun; ++slot) {
     const int t = seg_begin - 1 + slot;
-    float* fr = frames + slot * kFramePitch;
-    if (t < 0 || t >= n_frames) {                           // uniform per group
-      for (int i = j; i < kFramePitch; i += 64) fr[i] = 0.0f;
+    if (t >= n_frames) break;
+    if (t < 0) {                                                // no frame before the first: empty tail
+      for (int i = j; i < 256; i += 64) tail[i] = 0.0f;
+      group_bar(bar);
       continue;
     }
     const float* __restrict__ mrow = mag + (f0 + t) * SVS_N_BINS;
@@ -100,36 +105,30 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
       const int n = jj + 64 * d;
-      const float2 wv = make_float2(__ldg(&hann[2 * n]), __ldg(&hann[2 * n + 1]));
+      const float2 wv = __ldg(reinterpret_cast<const float2*>(hann) + n);
       *reinterpret_cast<float2*>(&fr[2 * n]) = make_float2(v[d].x * sc * wv.x, -v[d].y * sc * wv.y);
     }
-    group_bar(bar);                                          // buffers reused by this group's next frame
-  }
-  __syncthreads();
-
-  // ---- gather-form overlap-add: every output sample is written exactly once ----
-  const int64_t w0 = wave_off[song];
-  const int out_len = SVS_HOP * (n_frames - 1);             // librosa: hop * (T - 1) after trimming
-  float peak = 0.0f;
-  const int n_seg = min(kIstftSeg, n_frames - seg_begin);
-  for (int i = threadIdx.x; i < n_seg * SVS_HOP; i += kIstftThreads) {
-    const int s = i / SVS_HOP;
-    const int r = i - s * SVS_HOP;
-    const int t = seg_begin + s;
-    const int p = t * SVS_HOP + r - SVS_N_FFT / 2;          // output sample index
-    if (p < 0 || p >= out_len) continue;
-    const float cur = frames[(s + 1) * kFramePitch + r];
-    float val, env;
-    if (r < SVS_N_FFT - SVS_HOP && t > 0) {
-      val = frames[s * kFramePitch + r + SVS_HOP] + cur;    // frame t-1 was added first, then frame t
-      env = __ldg(&env_both[r]);
-    } else {
-      val = cur;
-      env = __ldg(&env_single[r]);
+    group_bar(bar);
+    // ---- emit hop segment t (gather form: frame t-1's tail + frame t), then keep frame t's tail ----
+    const bool emit = slot >= 1;                              // slot 0 is transformed only for its tail
+#pragma unroll
+    for (int c = 0; c < SVS_HOP / 64; ++c) {
+      const int r = j + 64 * c;
+      const float cur = fr[r];
+      if (emit) {
+        const int p = t * SVS_HOP + r - SVS_N_FFT / 2;        // output sample index
+        if (p >= 0 && p < out_len) {
+          float val;
+          if (r < SVS_N_FFT - SVS_HOP && t > 0) val = (tail[r] + cur) * __ldg(&env_both[r]);   // t-1 added first
+          else val = cur * __ldg(&env_single[r]);
+          wave[w0 + p] = val;
+          peak = fmaxf(peak, fabsf(val));
+        }
+      }
     }
-    if (env > 1.17549435e-38f) val = val / env;              // librosa: where env > tiny(float32)
-    wave[w0 + p] = val;
-    peak = fmaxf(peak, fabsf(val));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tail[j + 64 * c] = fr[SVS_HOP + j + 64 * c];   // same thread read tail[r] above
+    group_bar(bar);                                          // fr / scratch are rewritten by the next frame
   }
   if (song_peak != nullptr) {
     peak = warp_max(peak);
@@ -168,7 +167,7 @@ extern "C" int svs_istft_ola(const float* mag, const float* phase, const int64_t
   SVS_CUDA_TRY(cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(kIstftSmemBytes)));
   if (song_peak) SVS_CUDA_TRY(cudaMemsetAsync(song_peak, 0, sizeof(float) * n_songs, st));
-  dim3 grid(static_cast<unsigned>((max_frames + kIstftSeg - 1) / kIstftSeg), n_songs);
+  dim3 grid(static_cast<unsigned>((max_frames + 4 * kIstftRun - 1) / (4 * kIstftRun)), n_songs);
   istft_ola_kernel<<<grid, kIstftThreads, kIstftSmemBytes, st>>>(
       mag, reinterpret_cast<const float2*>(phase), frame_off, wave_off, wave, song_peak, tabs.tw1024,
       tabs.hann, tabs.env_both, tabs.env_single);

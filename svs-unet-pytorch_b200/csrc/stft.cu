@@ -18,8 +18,22 @@ namespace svs {
 constexpr int kStftThreads = 256;
 constexpr int kStftFramesPerCta = 32;     // 8 frames per 64-thread group
 
+// |x| and x/|x| (1+0j where |x| == 0, librosa.magphase) with one rsqrt instead of a sqrt and two divisions
+__device__ __forceinline__ void mag_phase(float2 x, float& m, float2& ph) {
+  const float m2 = x.x * x.x + x.y * x.y;
+  if (m2 > 1e-37f) {
+    const float inv = rsqrtf(m2);
+    m = m2 * inv;
+    ph = make_float2(x.x * inv, x.y * inv);
+  } else {                                   // zero / denormal energy: exact path (reference data.py:80 semantics)
+    m = sqrtf(m2);
+    const float z = (m == 0.0f) ? 1.0f : 0.0f;
+    ph = make_float2(x.x / (m + z) + z, x.y / (m + z));
+  }
+}
+
 template <bool kComplexOut>
-__global__ void __launch_bounds__(kStftThreads)
+__global__ void __launch_bounds__(kStftThreads, 2)
 stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict__ sample_off,
                       const int64_t* __restrict__ frame_off, float* __restrict__ mag,
                       float2* __restrict__ phase, float* __restrict__ song_max,
@@ -34,6 +48,7 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
   const int64_t s0 = sample_off[song];
   const int len = static_cast<int>(sample_off[song + 1] - s0);
   const float* __restrict__ y = audio + s0;
+  const bool vec2 = (reinterpret_cast<uintptr_t>(y) & 7) == 0;      // frame starts are even sample offsets
 
   const int group = threadIdx.x >> 6;
   const int j = threadIdx.x & 63;
@@ -64,8 +79,14 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) {
       const int i0 = base + 2 * (j + 64 * n1);
-      const float x0 = (i0 >= 0 && i0 < len) ? __ldg(&y[i0]) : 0.0f;
-      const float x1 = (i0 + 1 >= 0 && i0 + 1 < len) ? __ldg(&y[i0 + 1]) : 0.0f;
+      float x0, x1;
+      if (vec2 && i0 >= 0 && i0 + 1 < len) {
+        const float2 xv = __ldg(reinterpret_cast<const float2*>(y + i0));
+        x0 = xv.x; x1 = xv.y;
+      } else {
+        x0 = (i0 >= 0 && i0 < len) ? __ldg(&y[i0]) : 0.0f;
+        x1 = (i0 + 1 >= 0 && i0 + 1 < len) ? __ldg(&y[i0 + 1]) : 0.0f;
+      }
       v[n1] = make_float2(x0 * win[n1].x, x1 * win[n1].y);
     }
     fft512_group(v, tw, scratch, j, bar);
@@ -100,22 +121,18 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
         if (kk != k) prow[kk] = xkk;
       } else {
         {
-          const float m = sqrtf(xk.x * xk.x + xk.y * xk.y);
+          float m; float2 ph;
+          mag_phase(xk, m, ph);
           mrow[k] = m;
           run_max = fmaxf(run_max, m);
-          if (prow) {
-            const float z = (m == 0.0f) ? 1.0f : 0.0f;
-            prow[k] = make_float2(xk.x / (m + z) + z, xk.y / (m + z));
-          }
+          if (prow) prow[k] = ph;
         }
         if (kk != k) {
-          const float m = sqrtf(xkk.x * xkk.x + xkk.y * xkk.y);
+          float m; float2 ph;
+          mag_phase(xkk, m, ph);
           mrow[kk] = m;
           run_max = fmaxf(run_max, m);
-          if (prow) {
-            const float z = (m == 0.0f) ? 1.0f : 0.0f;
-            prow[kk] = make_float2(xkk.x / (m + z) + z, xkk.y / (m + z));
-          }
+          if (prow) prow[kk] = ph;
         }
       }
     }

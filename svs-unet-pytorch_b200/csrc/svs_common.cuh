@@ -39,8 +39,8 @@ int fail(int code, const std::string& msg);
 struct SpectralTables {
   const float2* tw1024;     // W_1024^m = exp(-2 pi i m / 1024), m in [0,1024)
   const float* hann;        // periodic Hann, 1024 (float64 rounded to float32)
-  const float* env_both;    // [256]  fl32(fl32(w^2[r+768]) + w^2[r])   two frames cover the sample
-  const float* env_single;  // [768]  fl32(w^2[r])                       one frame covers the sample
+  const float* env_both;    // [256]  1 / fl32(fl32(w^2[r+768]) + w^2[r])   two frames cover the sample
+  const float* env_single;  // [768]  1 / fl32(w^2[r])                       one frame covers the sample
 };
 int get_spectral_tables(SpectralTables* out);   // lazily builds the tables on the current device
 

@@ -15,11 +15,11 @@ def main():
     audio = torch.randn(n_songs * n, device="cuda") * 0.1
     batch = spectral.SongBatch(audio, [n] * n_songs)
     frames = batch.total_frames
-    for _ in range(3):
+    for _ in range(100):                       # ~0.2 s: let the SM clock ramp from idle before timing
         mag, phase, smax = batch.stft()
         wave, peak = batch.istft(mag, phase)
     torch.cuda.synchronize()
-    reps = 10
+    reps = 50
     for name, fn, bytes_per_frame in (("stft", lambda: batch.stft(), 9228), ("istft+ola", lambda: batch.istft(mag, phase), 9228)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
