@@ -52,12 +52,27 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
   }
 }
 
-struct FftTwiddles {
-  float2 a[7];   // W_512^{j*k1},  k1 = 1..7
-  float2 b[7];   // W_64^{(j&7)*c}, c = 1..7
+// Per-thread FFT twiddles live in a shared-memory table built once per CTA (they are the same for the
+// four frame groups): keeping them in registers cost 28 registers per thread and capped occupancy.
+//   a[k-1][j] = W_512^{j k}      (pass A, k = 1..7)
+//   b[c-1][j] = W_64^{(j&7) c}   (pass B, c = 1..7)
+constexpr int kFftTwiddleFloat2 = 2 * 7 * 64;
+
+struct FftTwiddles {                 // shared-memory table (iSTFT: frees 28 registers per thread)
+  const float2* a;
+  const float2* b;
+  int j;
+  __device__ __forceinline__ float2 ta(int k) const { return a[(k - 1) * 64 + j]; }
+  __device__ __forceinline__ float2 tb(int c) const { return b[(c - 1) * 64 + j]; }
 };
 
-__device__ __forceinline__ void load_fft_twiddles(FftTwiddles& tw, const float2* __restrict__ tw1024, int j) {
+struct FftTwiddlesReg {              // per-thread registers (STFT: shared-memory bandwidth is its limiter)
+  float2 a[7], b[7];
+  __device__ __forceinline__ float2 ta(int k) const { return a[k - 1]; }
+  __device__ __forceinline__ float2 tb(int c) const { return b[c - 1]; }
+};
+
+__device__ __forceinline__ void load_fft_twiddles(FftTwiddlesReg& tw, const float2* __restrict__ tw1024, int j) {
 #pragma unroll
   for (int k = 1; k < 8; ++k) {
     tw.a[k - 1] = __ldg(&tw1024[(2 * j * k) & 1023]);
@@ -65,12 +80,28 @@ __device__ __forceinline__ void load_fft_twiddles(FftTwiddles& tw, const float2*
   }
 }
 
+// all threads of the CTA cooperate; caller synchronises the CTA afterwards
+__device__ __forceinline__ FftTwiddles build_fft_twiddles(float2* table, const float2* __restrict__ tw1024,
+                                                          int tid, int nthreads, int j) {
+  for (int i = tid; i < 7 * 64; i += nthreads) {
+    const int k = i / 64 + 1, j = i % 64;
+    table[i] = __ldg(&tw1024[(2 * j * k) & 1023]);
+    table[7 * 64 + i] = __ldg(&tw1024[(16 * (j & 7) * k) & 1023]);
+  }
+  FftTwiddles tw;
+  tw.a = table;
+  tw.b = table + 7 * 64;
+  tw.j = j;
+  return tw;
+}
+
 __device__ __forceinline__ int z_addr(int k) { return k + 4 * (k >> 5); }
 
 // Forward FFT of the 64-thread group.  in: v[n1] = z[j + 64 n1].  out: v[d] = Z[jj + 64 d] with
 // jj = (j >> 3) + 8 (j & 7).  `scratch` = this group's kFftGroupFloats floats.  On return the
 // caller may overwrite buffer X only after a further group_bar (see callers).
-__device__ __forceinline__ void fft512_group(float2 (&v)[8], const FftTwiddles& tw, float* scratch, int j, int bar) {
+template <typename TW>
+__device__ __forceinline__ void fft512_group(float2 (&v)[8], const TW& tw, float* scratch, int j, int bar) {
   float* xre = scratch;
   float* xim = scratch + kFftScratchFloats;
   float* yre = scratch + 2 * kFftScratchFloats;
@@ -78,7 +109,7 @@ __device__ __forceinline__ void fft512_group(float2 (&v)[8], const FftTwiddles& 
   // pass A: radix-8 over n1, twiddle W_512^{j k1}
   dft8(v);
 #pragma unroll
-  for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw.a[k - 1]);
+  for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw.ta(k));
 #pragma unroll
   for (int k = 0; k < 8; ++k) { xre[k * 72 + j] = v[k].x; xim[k * 72 + j] = v[k].y; }
   group_bar(bar);
@@ -88,7 +119,7 @@ __device__ __forceinline__ void fft512_group(float2 (&v)[8], const FftTwiddles& 
   for (int a = 0; a < 8; ++a) { v[a].x = xre[k1 * 72 + 8 * a + b]; v[a].y = xim[k1 * 72 + 8 * a + b]; }
   dft8(v);
 #pragma unroll
-  for (int c = 1; c < 8; ++c) v[c] = cmul(v[c], tw.b[c - 1]);
+  for (int c = 1; c < 8; ++c) v[c] = cmul(v[c], tw.tb(c));
 #pragma unroll
   for (int c = 0; c < 8; ++c) { yre[(k1 * 8 + c) * 9 + b] = v[c].x; yim[(k1 * 8 + c) * 9 + b] = v[c].y; }
   group_bar(bar);

@@ -19,7 +19,7 @@ namespace svs {
 constexpr int kIstftThreads = 256;
 constexpr int kIstftRun = 16;                    // consecutive hop segments owned by one 64-thread group
 constexpr int kIstftGroupFloats = kFftGroupFloats + 1024 + 256;   // FFT scratch + windowed frame + previous tail
-constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats;
+constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats + sizeof(float2) * kFftTwiddleFloat2;
 
 // One 64-thread group walks kIstftRun + 1 consecutive frames of one song: frame t-1's last 256 windowed
 // samples (its "tail") stay in shared memory and are added to the first 256 samples of frame t when the
@@ -38,6 +38,9 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   const int group = threadIdx.x >> 6;
   const int j = threadIdx.x & 63;
   const int seg_begin = (blockIdx.x * 4 + group) * kIstftRun;   // first segment (= frame index) of this group
+  float2* tw_table = reinterpret_cast<float2*>(smem + 4 * kIstftGroupFloats);
+  const FftTwiddles tw = build_fft_twiddles(tw_table, tw1024, threadIdx.x, kIstftThreads, j);
+  __syncthreads();
   if (seg_begin >= n_frames) return;                            // whole group leaves (barriers are per group)
   float* scratch = smem + group * kIstftGroupFloats;
   float* xre = scratch;
@@ -46,8 +49,6 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   float* tail = fr + 1024;                                      // [256]  frame t-1, samples 768..1023
   const int bar = 1 + group;
 
-  FftTwiddles tw;
-  load_fft_twiddles(tw, tw1024, j);
   float2 twp[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) twp[q] = __ldg(&tw1024[j + 64 * q]);

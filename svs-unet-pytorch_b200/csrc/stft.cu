@@ -55,15 +55,13 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
   float* scratch = scratch_all + group * kFftGroupFloats;
   const int bar = 1 + group;
 
-  // per-thread constants: window taps, FFT twiddles, split-step twiddles
-  FftTwiddles tw;
+  // per-thread constants in registers: window taps, FFT twiddles, split-step twiddles (the kernel's limiter
+  // is shared-memory bandwidth, so tables in shared memory cost more than the occupancy they buy: measured)
+  FftTwiddlesReg tw;
   load_fft_twiddles(tw, tw1024, j);
   float2 win[8];
 #pragma unroll
-  for (int n1 = 0; n1 < 8; ++n1) {
-    const int n = j + 64 * n1;
-    win[n1] = make_float2(__ldg(&hann[2 * n]), __ldg(&hann[2 * n + 1]));
-  }
+  for (int n1 = 0; n1 < 8; ++n1) win[n1] = __ldg(reinterpret_cast<const float2*>(hann) + j + 64 * n1);
   float2 twp[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) twp[q] = __ldg(&tw1024[j + 64 * q]);
