@@ -2,6 +2,7 @@
 #include "svs_common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -24,6 +25,11 @@ int num_sms() {
     cached = n;
   }
   return cached;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SVS_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
 }
 
 namespace {

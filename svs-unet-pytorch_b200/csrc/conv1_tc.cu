@@ -64,10 +64,12 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     tma_prefetch_desc(&tmap_w);
   }
   if (warp == 4) tmem_alloc<64>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();                                     // the input may come from a preceding kernel; cat1 is reused across forwards
 
   if (warp == 4) {
     if (elect_one_sync()) {
@@ -247,18 +249,17 @@ int c1t_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_v
     constexpr size_t smem = c1t_smem_bytes<true>();
     SVS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    conv1_tc_kernel<float, true><<<grid, kC1tThreads, smem, st>>>(tin, plan->c1_tmap_w, plan->b_fold[0],
-                                                                  reinterpret_cast<float*>(ws.buf[g.out_buf]),
-                                                                  kBufGeom[g.out_buf].c, g.out_coff);
+    SVS_CUDA_TRY(launch_pdl(conv1_tc_kernel<float, true>, grid, dim3(kC1tThreads), smem, st, tin, plan->c1_tmap_w,
+                            static_cast<const float*>(plan->b_fold[0]), reinterpret_cast<float*>(ws.buf[g.out_buf]),
+                            kBufGeom[g.out_buf].c, g.out_coff));
   } else {
     constexpr size_t smem = c1t_smem_bytes<false>();
     SVS_CUDA_TRY(cudaFuncSetAttribute(conv1_tc_kernel<__nv_bfloat16, false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    conv1_tc_kernel<__nv_bfloat16, false><<<grid, kC1tThreads, smem, st>>>(
-        tin, plan->c1_tmap_w, plan->b_fold[0], reinterpret_cast<__nv_bfloat16*>(ws.buf[g.out_buf]),
-        kBufGeom[g.out_buf].c, g.out_coff);
+    SVS_CUDA_TRY(launch_pdl(conv1_tc_kernel<__nv_bfloat16, false>, grid, dim3(kC1tThreads), smem, st, tin,
+                            plan->c1_tmap_w, static_cast<const float*>(plan->b_fold[0]),
+                            reinterpret_cast<__nv_bfloat16*>(ws.buf[g.out_buf]), kBufGeom[g.out_buf].c, g.out_coff));
   }
-  SVS_CHECK_LAUNCH("conv1_tc_kernel");
   return SVS_OK;
 }
 

@@ -126,6 +126,8 @@ conv1_kernel(const float* __restrict__ in, const int64_t* __restrict__ patch_off
   __shared__ __align__(16) float sw[25 * 16];
   __shared__ __align__(16) float sb[16];
   __shared__ __align__(16) float tile[kC1InRows * kC1Pitch];
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < 400; i += kC1Threads) sw[i] = w[i];
   if (threadIdx.x < 16) sb[threadIdx.x] = bias[threadIdx.x];
   const int b = blockIdx.y;

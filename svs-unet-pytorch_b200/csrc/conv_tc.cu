@@ -138,11 +138,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_b0);
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+  pdl_wait();                                     // previous layer complete: activations readable, outputs writable
 
   if (warp == 0) {
     // ===== TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
@@ -327,6 +329,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const TcParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cg_n = p.cout >> 2;
   const size_t total = static_cast<size_t>(p.n_phases) * p.m_pad * cg_n;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -636,8 +640,8 @@ static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p,
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  kern<<<grid, kTcThreads, smem, st>>>(ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2], t.tmap_b[3], p);
-  SVS_CHECK_LAUNCH("tc_conv_kernel");
+  SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, st, ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2],
+                          t.tmap_b[3], p));
   return SVS_OK;
 }
 
@@ -717,9 +721,8 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   if (split > 1) {
     const size_t total = static_cast<size_t>(t.n_phases) * p.m_pad * (g.cout / 4);
     const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-    if (tf32) splitk_finish_kernel<float><<<blocks, 256, 0, st>>>(p);
-    else splitk_finish_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
-    SVS_CHECK_LAUNCH("splitk_finish_kernel");
+    if (tf32) SVS_CUDA_TRY(launch_pdl(splitk_finish_kernel<float>, dim3(blocks), dim3(256), 0, st, p));
+    else SVS_CUDA_TRY(launch_pdl(splitk_finish_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, p));
   }
   return SVS_OK;
 }

@@ -66,10 +66,12 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_w);
   }
   if (warp == 1) tmem_alloc<128>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -222,18 +224,19 @@ int d6_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_vi
     constexpr size_t smem = d6_smem_bytes<128>();
     SVS_CUDA_TRY(cudaFuncSetAttribute(deconv6_tc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    deconv6_tc_kernel<true, 128><<<grid, kD6Threads, smem, st>>>(
-        ta, plan->d6_tmap_w, plan->b_fold[11], in->base, in->patch_off, in->stride_b, in->stride_f, in->stride_t,
-        out->base, out->patch_off, out->stride_b, out->stride_f, out->stride_t, in_frames, flags);
+    SVS_CUDA_TRY(launch_pdl(deconv6_tc_kernel<true, 128>, grid, dim3(kD6Threads), smem, st, ta, plan->d6_tmap_w,
+                            static_cast<const float*>(plan->b_fold[11]), static_cast<const float*>(in->base),
+                            in->patch_off, in->stride_b, in->stride_f, in->stride_t, out->base, out->patch_off,
+                            out->stride_b, out->stride_f, out->stride_t, in_frames, flags));
   } else {
     constexpr size_t smem = d6_smem_bytes<64>();
     SVS_CUDA_TRY(cudaFuncSetAttribute(deconv6_tc_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    deconv6_tc_kernel<false, 64><<<grid, kD6Threads, smem, st>>>(
-        ta, plan->d6_tmap_w, plan->b_fold[11], in->base, in->patch_off, in->stride_b, in->stride_f, in->stride_t,
-        out->base, out->patch_off, out->stride_b, out->stride_f, out->stride_t, in_frames, flags);
+    SVS_CUDA_TRY(launch_pdl(deconv6_tc_kernel<false, 64>, grid, dim3(kD6Threads), smem, st, ta, plan->d6_tmap_w,
+                            static_cast<const float*>(plan->b_fold[11]), static_cast<const float*>(in->base),
+                            in->patch_off, in->stride_b, in->stride_f, in->stride_t, out->base, out->patch_off,
+                            out->stride_b, out->stride_f, out->stride_t, in_frames, flags));
   }
-  SVS_CHECK_LAUNCH("deconv6_tc_kernel");
   return SVS_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 #include "svs_b200.h"
 
@@ -45,6 +46,26 @@ struct SpectralTables {
 int get_spectral_tables(SpectralTables* out);   // lazily builds the tables on the current device
 
 int num_sms();
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Every layer kernel is launched with programmaticStreamSerialization so that its prologue (barrier
+// init, TMEM allocation, tensor-map prefetch, resident weights) overlaps the tail of the previous
+// layer; inside the kernel pdl_wait() blocks until the previous grid has completed and flushed, and
+// must precede the first access to anything that grid wrote (or reads and this grid overwrites).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- small device helpers --------------------------------------------------------------------
 __device__ __forceinline__ float warp_max(float v) {

@@ -136,6 +136,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_b);
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,6 +153,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         __syncwarp();
       }
+      pdl_wait();                                 // activations of the previous layer from here on
       // slab jobs are numbered across tiles; the slab of job j+1 is requested BEFORE the weight chunks
       // of job j so the halo loads run one slab ahead of the MMAs
       auto issue_a = [&](int ja, int tile, int s) {
@@ -302,6 +304,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
   } else {
     // ===== epilogue =====
+    pdl_wait();                                   // before the first global store
     const int q = warp & 3;
     const int r = 32 * q + lane;
     const int ix = r & 7, iy = r >> 3;
@@ -512,8 +515,7 @@ static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcPar
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > p.m_tiles) grid = p.m_tiles;
-  kern<<<grid, kZcThreads, smem, st>>>(ta, tb, p);
-  SVS_CHECK_LAUNCH("zc_conv_kernel");
+  SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, ta, tb, p));
   return SVS_OK;
 }
 
