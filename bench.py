@@ -281,6 +281,11 @@ def run_ours(args):
         tc_ms = sum(layer_ms[li] for li in tc_layers)
         achieved = tc_flops / (tc_ms * 1e-3) / 1e12
         launches = plan.launch_count(BATCH)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):                                     # DRAM bytes of the same kernels from the committed ncu capture
+            with open(tpath) as f:
+                traffic = json.load(f).get("tc_conv_family_dram_bytes_per_forward")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -298,7 +303,8 @@ def run_ours(args):
             "launches_per_step": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                         "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                         "traffic_note": "dram read+write bytes summed over the 10 conv2..deconv5 launches of one 64-patch forward (ncu --set full, cold L2); algorithmic activation bytes: 2 x 64 x 0.98 M bf16 elements = 251 MB + 41 MB weights",
                          "kernel": "tc_conv_kernel (tcgen05 implicit GEMM, conv2..deconv5)",
                          "peak_source": peaks["source"] + " bf16_tflops_sustained",
                          "flops": "exact valid-tap count of the layers the kernel executes"},
