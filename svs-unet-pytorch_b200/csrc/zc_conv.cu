@@ -563,11 +563,11 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
 #define SVS_ZC_STATIC(LI, N, AS, BS, RES, TAPS)                                                     \
   if (!tf32 && li == LI && n == N && z.resident == RES && z.sch.n_slabs == TAPS::kSlabs)              \
     return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);
-  SVS_ZC_STATIC(1, 32, 4, 15, true, ZcConv2Taps)
-  SVS_ZC_STATIC(2, 64, 5, 8, false, ZcConvParityTaps<0xC>)
+  SVS_ZC_STATIC(1, 32, 2, 15, true, ZcConv2Taps)              // 2 CTAs / SM: one CTA's epilogue hides the other's loads
+  SVS_ZC_STATIC(2, 64, 3, 4, false, ZcConvParityTaps<0xC>)
   SVS_ZC_STATIC(3, 128, 5, 6, false, ZcConvParityTaps<0xF>)
   SVS_ZC_STATIC(8, 256, 3, 4, false, ZcDeconvTaps<4>)
-  SVS_ZC_STATIC(9, 128, 5, 6, false, ZcDeconvTaps<2>)
+  SVS_ZC_STATIC(9, 128, 2, 3, false, ZcDeconvTaps<2>)
   SVS_ZC_STATIC(10, 64, 4, 9, true, ZcDeconvTaps<1>)
 #undef SVS_ZC_STATIC
 #define SVS_ZC_CASE(N, AS, BS, RES)                                                               \
