@@ -94,7 +94,7 @@ struct TcLayer {
 };
 
 // ---- zero-copy tcgen05 layers (zc_conv.cu) -------------------------------------------------------
-constexpr int kZcMaxTaps = 64, kZcMaxSlabs = 8;
+constexpr int kZcMaxTaps = 80, kZcMaxSlabs = 8;
 struct ZcSchedule {
   int n_slabs, n_taps;
   int slab_c[kZcMaxSlabs], slab_ph[kZcMaxSlabs];   // TMA coordinates (channel window, row parity) of each halo slab

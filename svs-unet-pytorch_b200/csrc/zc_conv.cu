@@ -88,6 +88,10 @@ template <int kNSlabs> struct ZcDeconvTaps {      // phase-merged deconv: every 
 struct ZcConv2Taps {                              // Ct = 32: row = [pw0: d-half | skip | pw1: d-half | skip]; slab = ph
   static constexpr bool kStatic = true; static constexpr int kSlabs = 2;
   __host__ __device__ static constexpr int kmask(int s, int dy, int dx) { return (2 * dy + s + 2 > 4) ? 0 : (dx <= 0 ? 0xA : 0x2); } };
+struct ZcConvParity2Taps {                        // two 128-byte channel windows per column parity (TF32 conv4):
+  static constexpr bool kStatic = true; static constexpr int kSlabs = 8;   // slab = ph*4 + pw*2 + window
+  __host__ __device__ static constexpr int kmask(int s, int dy, int dx) {
+    return (2 * dy + (s >> 2) + 2 > 4 || 2 * dx + ((s >> 1) & 1) + 2 > 4) ? 0 : 0xF; } };
 template <int kKMask> struct ZcConvParityTaps {   // slabs (ph, pw) = (s >> 1, s & 1): conv3 (skip half = 0xC), conv4 (0xF)
   static constexpr bool kStatic = true; static constexpr int kSlabs = 4;
   __host__ __device__ static constexpr int kmask(int s, int dy, int dx) {
@@ -560,15 +564,24 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   const int n = z.n_total;
   // bf16 layers of the reference network get compile-time tap tables; anything else (TF32 rows are 32
   // channels wide, so the slab/tap sets differ) runs the same kernel with the runtime schedule
-#define SVS_ZC_STATIC(LI, N, AS, BS, RES, TAPS)                                                     \
-  if (!tf32 && li == LI && n == N && z.resident == RES && z.sch.n_slabs == TAPS::kSlabs)              \
-    return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);
-  SVS_ZC_STATIC(1, 32, 2, 15, true, ZcConv2Taps)              // 2 CTAs / SM: one CTA's epilogue hides the other's loads
-  SVS_ZC_STATIC(2, 64, 3, 4, false, ZcConvParityTaps<0xC>)
-  SVS_ZC_STATIC(3, 128, 5, 6, false, ZcConvParityTaps<0xF>)
-  SVS_ZC_STATIC(8, 256, 3, 4, false, ZcDeconvTaps<4>)
-  SVS_ZC_STATIC(9, 128, 2, 3, false, ZcDeconvTaps<2>)
-  SVS_ZC_STATIC(10, 64, 4, 9, true, ZcDeconvTaps<1>)
+#define SVS_ZC_STATIC(TF, LI, N, AS, BS, RES, TAPS)                                                 \
+  if (tf32 == TF && li == LI && n == N && z.resident == RES && z.sch.n_slabs == TAPS::kSlabs) {       \
+    if constexpr (TF) return zc_launch_t<float, true, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);          \
+    else return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);              \
+  }
+  SVS_ZC_STATIC(false, 1, 32, 2, 15, true, ZcConv2Taps)       // 2 CTAs / SM: one CTA's epilogue hides the other's loads
+  SVS_ZC_STATIC(false, 2, 64, 3, 4, false, ZcConvParityTaps<0xC>)
+  SVS_ZC_STATIC(false, 3, 128, 5, 6, false, ZcConvParityTaps<0xF>)
+  SVS_ZC_STATIC(false, 8, 256, 3, 4, false, ZcDeconvTaps<4>)
+  SVS_ZC_STATIC(false, 9, 128, 2, 3, false, ZcDeconvTaps<2>)
+  SVS_ZC_STATIC(false, 10, 64, 4, 9, true, ZcDeconvTaps<1>)
+  // TF32: 128-byte rows hold 32 channels, so every layer has twice the slabs of its bf16 form
+  SVS_ZC_STATIC(true, 1, 32, 3, 8, false, ZcConvParityTaps<0xC>)
+  SVS_ZC_STATIC(true, 2, 64, 3, 4, false, ZcConvParityTaps<0xF>)
+  SVS_ZC_STATIC(true, 3, 128, 4, 4, false, ZcConvParity2Taps)
+  SVS_ZC_STATIC(true, 8, 256, 3, 4, false, ZcDeconvTaps<8>)
+  SVS_ZC_STATIC(true, 9, 128, 4, 4, false, ZcDeconvTaps<4>)
+  SVS_ZC_STATIC(true, 10, 64, 3, 6, false, ZcDeconvTaps<2>)
 #undef SVS_ZC_STATIC
 #define SVS_ZC_CASE(N, AS, BS, RES)                                                               \
   if (n == N && z.resident == RES && (!RES || z.sch.n_taps == BS))                                 \
