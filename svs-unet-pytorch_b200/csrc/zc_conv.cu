@@ -45,7 +45,6 @@ struct ZcParams {
   int cout_phase, merged, act;
   int resident;                  // weights resident in smem
   long long* dbg;                // profiling: per CTA 64 clock64 stamps
-  int exp_mode;                  // experiments only (wrong numerics): 1 = unshifted start, 2 = + canonical SBO
 };
 
 template <int kBlockN, int kASlots, int kBSlots>
@@ -275,10 +274,8 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tc_fence_after();
               b_addr = b_base + bs * kBBytes;
             }
-            uint32_t a_addr = a_base + ((p.sch.tap_dy[tap] + 1) * kZcPw + (p.sch.tap_dx[tap] + 1)) * 128;
-            uint32_t sbo = kZcPw * 128;
-            if (p.exp_mode >= 1) a_addr = a_base;
-            if (p.exp_mode >= 2) sbo = 1024;
+            const uint32_t a_addr = a_base + ((p.sch.tap_dy[tap] + 1) * kZcPw + (p.sch.tap_dx[tap] + 1)) * 128;
+            const uint32_t sbo = kZcPw * 128;
             // SW128 K-major; 8-row groups (one image row) are 10 slab rows = 1280 B apart; base_offset 0
             const uint64_t da = static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4) | (1ull << 16) |
                                 (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -560,7 +557,6 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   p.act = g.act;
   p.resident = z.resident ? 1 : 0;
   p.dbg = (g_tc_dbg_layer == li) ? g_tc_dbg : nullptr;
-  { const char* e = std::getenv("SVS_ZC_EXP"); p.exp_mode = e ? std::atoi(e) : 0; }
   const int n = z.n_total;
   // bf16 layers of the reference network get compile-time tap tables; anything else (TF32 rows are 32
   // channels wide, so the slab/tap sets differ) runs the same kernel with the runtime schedule
