@@ -70,23 +70,28 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
   float* xim = scratch + kFftScratchFloats;
   float run_max = 0.0f;
 
-  for (int t = t_begin + group; t < t_end; t += 4) {
-    // ---- load + window (frame t covers samples [768 t - 512, 768 t + 512)) ----
-    float2 v[8];
-    const int base = t * SVS_HOP - SVS_N_FFT / 2;
+  // software pipeline: the raw samples of this group's NEXT frame are requested before the current frame's FFT,
+  // so their DRAM latency overlaps the three radix passes (16 warps / SM cannot hide it by occupancy alone)
+  auto load_frame = [&](int t, float2 (&raw)[8]) {
+    const int base = t * SVS_HOP - SVS_N_FFT / 2;          // frame t covers samples [768 t - 512, 768 t + 512)
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) {
       const int i0 = base + 2 * (j + 64 * n1);
-      float x0, x1;
       if (vec2 && i0 >= 0 && i0 + 1 < len) {
-        const float2 xv = __ldg(reinterpret_cast<const float2*>(y + i0));
-        x0 = xv.x; x1 = xv.y;
+        raw[n1] = __ldg(reinterpret_cast<const float2*>(y + i0));
       } else {
-        x0 = (i0 >= 0 && i0 < len) ? __ldg(&y[i0]) : 0.0f;
-        x1 = (i0 + 1 >= 0 && i0 + 1 < len) ? __ldg(&y[i0 + 1]) : 0.0f;
+        raw[n1].x = (i0 >= 0 && i0 < len) ? __ldg(&y[i0]) : 0.0f;
+        raw[n1].y = (i0 + 1 >= 0 && i0 + 1 < len) ? __ldg(&y[i0 + 1]) : 0.0f;
       }
-      v[n1] = make_float2(x0 * win[n1].x, x1 * win[n1].y);
     }
+  };
+  float2 nxt[8];
+  if (t_begin + group < t_end) load_frame(t_begin + group, nxt);
+  for (int t = t_begin + group; t < t_end; t += 4) {
+    float2 v[8];
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) v[n1] = make_float2(nxt[n1].x * win[n1].x, nxt[n1].y * win[n1].y);
+    if (t + 4 < t_end) load_frame(t + 4, nxt);
     fft512_group(v, tw, scratch, j, bar);
     // ---- exchange 3: Z[k] in padded linear order ----
     const int jj = (j >> 3) + 8 * (j & 7);
