@@ -21,6 +21,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
 #include "unet_internal.cuh"
 #include "tc_ptx.cuh"
+#include "tc_conv_common.cuh"
 
 #include <cudaTypedefs.h>
 #include <type_traits>
@@ -29,51 +30,6 @@
 
 namespace svs {
 
-// ---------------------------------------------------------------------------------------------
-struct TcParams {
-  const TcChunk* chunks;
-  int n_chunks[4], chunk_begin[4], py[4], px[4];
-  int n_phases, split_k;
-  int ntw, nth;                  // M tiles along w and h of the pixel grid
-  int m_tiles, n_tiles;          // tile counts (M includes the batch dimension)
-  int bw, bh, nb;
-  int batch;
-  int block_k;                   // K elements per chunk
-  void* out;
-  int out_pitch, out_coff, hout, wout, out_scale;
-  const float* bias;
-  int act;
-  float* partial;
-  int m_pad;                     // rows per (phase, split) slab of `partial`
-  int cout;                      // GEMM N (merged deconv: 4 x channels)
-  int merged;                    // 1: N = 4 phases x cout_phase channels
-  int cout_phase;
-  long long* dbg;                // optional per-CTA clock64 trace (8 slots per CTA), profiling only
-};
-
-__device__ __forceinline__ float tc_act(float v, int act) {
-  if (act == ACT_LEAKY) return v > 0.0f ? v : 0.2f * v;
-  if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  return v;
-}
-__device__ __forceinline__ void store16(__nv_bfloat16* dst, const float (&f)[16]) {
-  uint32_t w[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    w[i] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  d[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  d[1] = make_uint4(w[4], w[5], w[6], w[7]);
-}
-__device__ __forceinline__ void store16(float* dst, const float (&f)[16]) {
-  float4* d = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) d[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-}
-
-constexpr int kTcThreads = 192;
 
 template <int kBlockN, int kSwz, int kStages>
 constexpr size_t tc_smem_bytes() {
