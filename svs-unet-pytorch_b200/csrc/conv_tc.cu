@@ -85,7 +85,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int total_tiles = per_z * p.n_phases * p.split_k;
 
   long long* dbg = p.dbg ? p.dbg + 8 * blockIdx.x : nullptr;
-  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  if (dbg && threadIdx.x == 0) dbg[0] = dbg_now();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
@@ -99,7 +99,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
-  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+  if (dbg && threadIdx.x == 0) dbg[1] = dbg_now();
   pdl_wait();                                     // previous layer complete: activations readable, outputs writable
 
   if (warp == 0) {
@@ -154,7 +154,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int s = it % kStages;
           const uint32_t par = (it / kStages) & 1;
           mbar_wait(full_bar(s), par);
-          if (dbg && it == 0 && lane == 0) dbg[2] = clock64();
+          if (dbg && it == 0 && lane == 0) dbg[2] = dbg_now();
           tc_fence_after();
           // dispatch on the stage index so that descriptors are "uniform base + compile-time constant":
           // descriptor arithmetic in the vector datapath costs an R2UR chain per MMA (see zc_conv.cu)
@@ -177,7 +177,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if (elect_one_sync()) umma_commit(tmem_full_bar(as));   // accumulator complete
         __syncwarp();
-        if (dbg && t == 0 && lane == 0) dbg[3] = clock64();
+        if (dbg && t == 0 && lane == 0) dbg[3] = dbg_now();
       }
     }
     __syncwarp();
@@ -203,7 +203,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool valid = b < p.batch;
       const int as = t & 1;
       mbar_wait(tmem_full_bar(as), (t >> 1) & 1);
-      if (dbg && t == 0 && threadIdx.x == 64) dbg[4] = clock64();
+      if (dbg && t == 0 && threadIdx.x == 64) dbg[4] = dbg_now();
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccCols;
       if (p.split_k == 1) {
@@ -269,12 +269,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(as));      // 4 warps -> accumulator stage is free
-      if (dbg && t == 0 && threadIdx.x == 64) dbg[5] = clock64();
+      if (dbg && t == 0 && threadIdx.x == 64) dbg[5] = dbg_now();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (dbg && threadIdx.x == 0) dbg[6] = clock64();
+  if (dbg && threadIdx.x == 0) dbg[6] = dbg_now();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
@@ -526,9 +526,16 @@ int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
       int rc = encode_tensor_map(&t.tmap_b[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides, box,
                           t.swz);
       if (rc != SVS_OK) return rc;
+      t.tmap_b_half[ph] = t.tmap_b[ph];
+      if (t.block_n == 128) {
+        const cuuint32_t box_half[2] = {static_cast<cuuint32_t>(t.block_k), 64u};
+        rc = encode_tensor_map(&t.tmap_b_half[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides,
+                               box_half, t.swz);
+        if (rc != SVS_OK) return rc;
+      }
       off += n;
     }
-    for (int ph = t.n_phases; ph < 4; ++ph) t.tmap_b[ph] = t.tmap_b[0];
+    for (int ph = t.n_phases; ph < 4; ++ph) { t.tmap_b[ph] = t.tmap_b[0]; t.tmap_b_half[ph] = t.tmap_b_half[0]; }
     SVS_CUDA_TRY(cudaStreamSynchronize(st));     // d_src / host vectors are consumed
     SVS_CUDA_TRY(cudaFree(d_src));
     t.enabled = true;
@@ -545,6 +552,22 @@ void tc_free_layers(svs_unet_plan* plan) {
   }
 }
 
+// SVS_TC_CLUSTER: 0 = one CTA per tile stream + split-K finish kernel, 1 = TMA-multicast clusters (experimental),
+// 2 (default) = split-K across a cluster with a DSMEM reduction (conv_tc_cluster.cu)
+static int ilog2_exact(int v) {      // log2 of a power of two, else -1
+  for (int k = 0; k < 31; ++k) if ((1 << k) == v) return k;
+  return -1;
+}
+int tc_cluster_mode() {
+  static const int mode = [] { const char* e = std::getenv("SVS_TC_CLUSTER"); return e ? std::atoi(e) : 2; }();
+  return mode;
+}
+bool ck_supported(const svs_unet_plan* plan, int li, int split);
+int ck_launch_layer(const svs_unet_plan* plan, int li, const CUtensorMap& ta, const TcParams& p, cudaStream_t st);
+bool mc_supported(const svs_unet_plan* plan, int li, int batch);
+int mc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, const TcParams& p,
+                    cudaStream_t st);
+
 void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, int* split_k) {
   const int ntw = t.gw / t.bw, nth = t.gh / t.bh, ntb = (batch + t.nb - 1) / t.nb;
   *m_tiles = ntw * nth * ntb;
@@ -558,6 +581,9 @@ void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, in
   else if (tiles < 120) s = 148 / tiles;
   if (s > 8) s = 8;
   if (s > min_chunks / 4) s = min_chunks / 4;
+  if (tc_cluster_mode() == 2 && !e) {               // cluster split-K reduces 128 / s rows per CTA
+    while (s & (s - 1)) --s;
+  }
   if (s < 1 || t.merged) s = 1;
   *split_k = s;
 }
@@ -580,6 +606,7 @@ size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch) {
 int tc_launch_count(const svs_unet_plan* plan, int li, int batch) {
   int m_tiles, split;
   tc_tiling(plan->tc[li], kLayers[li], batch, &m_tiles, &split);
+  if (split > 1 && tc_cluster_mode() == 2 && ck_supported(plan, li, split)) return 1;
   return split > 1 ? 2 : 1;   // main kernel (+ split-K reduction)
 }
 
@@ -596,6 +623,19 @@ static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p,
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = total_tiles;
+  static const int fake_cluster = [] { const char* e = std::getenv("SVS_TC_FAKE_CLUSTER"); return e ? std::atoi(e) : 0; }();
+  if (fake_cluster > 1 && grid % fake_cluster == 0) {   // experiment: cost of a cluster launch by itself
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = fake_cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    SVS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2], t.tmap_b[3], p));
+    return SVS_OK;
+  }
   SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, st, ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2],
                           t.tmap_b[3], p));
   return SVS_OK;
@@ -635,6 +675,7 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   p.split_k = split;
   p.ntw = t.gw / t.bw; p.nth = t.gh / t.bh;
   p.bw = t.bw; p.bh = t.bh; p.nb = t.nb;
+  p.bw_log2 = ilog2_exact(t.bw); p.bh_log2 = ilog2_exact(t.bh);
   p.batch = batch;
   p.block_k = t.block_k;
   p.out = ws.buf[g.out_buf];
@@ -656,8 +697,15 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   p.n_tiles = p.cout / t.block_n;
   const int grid = m_tiles * p.n_tiles * t.n_phases * split;
   int rc = SVS_ERR_NOT_IMPLEMENTED;
+  bool finish = split > 1;
+  if (tc_cluster_mode() == 2 && split > 1 && ck_supported(plan, li, split)) {
+    rc = ck_launch_layer(plan, li, ta, p, st);          // split-K inside a cluster: no partials, no finish kernel
+    finish = false;
+  } else if (tc_cluster_mode() == 1 && mc_supported(plan, li, batch)) {
+    rc = mc_launch_layer(plan, li, ws, batch, p, st);   // TMA multicast (experimental)
+  }
 #define SVS_TC_CASE(N, S, ST)                                                                       \
-  if (t.block_n == N && t.swz == S) {                                                               \
+  if (rc == SVS_ERR_NOT_IMPLEMENTED && t.block_n == N && t.swz == S) { \
     rc = tf32 ? launch_tc<float, true, N, S, ST>(ta, t, p, grid, st)                                \
               : launch_tc<__nv_bfloat16, false, N, S, ST>(ta, t, p, grid, st);                      \
   }
@@ -674,7 +722,7 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     return fail(rc, "tc_launch_layer: no kernel instantiation for block_n=" + std::to_string(t.block_n) +
                         " swz=" + std::to_string(t.swz));
   if (rc != SVS_OK) return rc;
-  if (split > 1) {
+  if (finish) {
     const size_t total = static_cast<size_t>(t.n_phases) * p.m_pad * (g.cout / 4);
     const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
     if (tf32) SVS_CUDA_TRY(launch_pdl(splitk_finish_kernel<float>, dim3(blocks), dim3(256), 0, st, p));

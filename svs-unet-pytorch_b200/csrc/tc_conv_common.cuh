@@ -15,6 +15,7 @@ struct TcParams {
   int ntw, nth;                  // M tiles along w and h of the pixel grid
   int m_tiles, n_tiles;          // tile counts (M includes the batch dimension)
   int bw, bh, nb;
+  int bw_log2, bh_log2;          // log2 of bw / bh when they are powers of two, else -1
   int batch;
   int block_k;                   // K elements per chunk
   void* out;
@@ -29,6 +30,12 @@ struct TcParams {
   long long* dbg;                // optional per-CTA clock64 trace (8 slots per CTA), profiling only
 };
 
+// profiling timestamps: %globaltimer (ns, one clock for the whole GPU) so that CTAs on different SMs compare
+__device__ __forceinline__ long long dbg_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ float tc_act(float v, int act) {
   if (act == ACT_LEAKY) return v > 0.0f ? v : 0.2f * v;
   if (act == ACT_RELU) return fmaxf(v, 0.0f);

@@ -31,14 +31,14 @@ def main():
         lib.svs_debug_set_trace(None, -1)
         t = buf.view(-1, 8).cpu()
         t = t[t[:, 0] > 0]
-        rel = (t[:, 1:7] - t[:, 0:1]).float()
-        names = ["setup", "first_full", "mma_issued", "acc_ready", "epi_done", "exit"]
-        print(f"layer {li}: {t.shape[0]} CTAs; median cycles since CTA start:")
+        t0 = t[:, 0].min()
+        names = ["start", "setup", "first_full", "mma_issued", "acc_ready", "epi_done", "exit", "parked_sync"]
+        print(f"layer {li}: {t.shape[0]} CTAs; ns since the first CTA started (globaltimer):")
         for i, n in enumerate(names):
-            col = rel[:, i]
-            print(f"   {n:11s} median {col.median().item():9.0f}  min {col.min().item():9.0f}  max {col.max().item():9.0f}")
-        span = (t[:, 6].max() - t[:, 0].min()).item()
-        print(f"   kernel span (clock64 across SMs, approximate): {span}")
+            col = t[:, i]
+            col = (col[col > 0] - t0).float()
+            if col.numel():
+                print(f"   {n:11s} median {col.median().item():9.0f}  min {col.min().item():9.0f}  max {col.max().item():9.0f}")
 
 
 if __name__ == "__main__":
