@@ -526,16 +526,9 @@ int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
       int rc = encode_tensor_map(&t.tmap_b[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides, box,
                           t.swz);
       if (rc != SVS_OK) return rc;
-      t.tmap_b_half[ph] = t.tmap_b[ph];
-      if (t.block_n == 128) {
-        const cuuint32_t box_half[2] = {static_cast<cuuint32_t>(t.block_k), 64u};
-        rc = encode_tensor_map(&t.tmap_b_half[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides,
-                               box_half, t.swz);
-        if (rc != SVS_OK) return rc;
-      }
       off += n;
     }
-    for (int ph = t.n_phases; ph < 4; ++ph) { t.tmap_b[ph] = t.tmap_b[0]; t.tmap_b_half[ph] = t.tmap_b_half[0]; }
+    for (int ph = t.n_phases; ph < 4; ++ph) t.tmap_b[ph] = t.tmap_b[0];
     SVS_CUDA_TRY(cudaStreamSynchronize(st));     // d_src / host vectors are consumed
     SVS_CUDA_TRY(cudaFree(d_src));
     t.enabled = true;
@@ -552,8 +545,8 @@ void tc_free_layers(svs_unet_plan* plan) {
   }
 }
 
-// SVS_TC_CLUSTER: 0 = one CTA per tile stream + split-K finish kernel, 1 = TMA-multicast clusters (experimental),
-// 2 (default) = split-K across a cluster with a DSMEM reduction (conv_tc_cluster.cu)
+// SVS_TC_CLUSTER: 0 = one CTA per tile stream + split-K finish kernel,
+// 2 (default) = split-K across a cluster, reduced through distributed shared memory (conv_tc_cluster.cu)
 static int ilog2_exact(int v) {      // log2 of a power of two, else -1
   for (int k = 0; k < 31; ++k) if ((1 << k) == v) return k;
   return -1;
@@ -564,9 +557,6 @@ int tc_cluster_mode() {
 }
 bool ck_supported(const svs_unet_plan* plan, int li, int split);
 int ck_launch_layer(const svs_unet_plan* plan, int li, const CUtensorMap& ta, const TcParams& p, cudaStream_t st);
-bool mc_supported(const svs_unet_plan* plan, int li, int batch);
-int mc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, const TcParams& p,
-                    cudaStream_t st);
 
 void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, int* split_k) {
   const int ntw = t.gw / t.bw, nth = t.gh / t.bh, ntb = (batch + t.nb - 1) / t.nb;
@@ -623,19 +613,6 @@ static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p,
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  static const int fake_cluster = [] { const char* e = std::getenv("SVS_TC_FAKE_CLUSTER"); return e ? std::atoi(e) : 0; }();
-  if (fake_cluster > 1 && grid % fake_cluster == 0) {   // experiment: cost of a cluster launch by itself
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = fake_cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    SVS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2], t.tmap_b[3], p));
-    return SVS_OK;
-  }
   SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, st, ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2],
                           t.tmap_b[3], p));
   return SVS_OK;
@@ -701,8 +678,6 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   if (tc_cluster_mode() == 2 && split > 1 && ck_supported(plan, li, split)) {
     rc = ck_launch_layer(plan, li, ta, p, st);          // split-K inside a cluster: no partials, no finish kernel
     finish = false;
-  } else if (tc_cluster_mode() == 1 && mc_supported(plan, li, batch)) {
-    rc = mc_launch_layer(plan, li, ws, batch, p, st);   // TMA multicast (experimental)
   }
 #define SVS_TC_CASE(N, S, ST)                                                                       \
   if (rc == SVS_ERR_NOT_IMPLEMENTED && t.block_n == N && t.swz == S) { \

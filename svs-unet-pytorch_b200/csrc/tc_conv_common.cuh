@@ -1,5 +1,5 @@
 // Shared between the tcgen05 implicit-GEMM kernels of conv_tc.cu (one CTA per tile stream) and
-// conv_tc_mc.cu (2x2 / 2x1 clusters with TMA multicast).
+// conv_tc_cluster.cu (split-K across a thread-block cluster).
 #pragma once
 #include "unet_internal.cuh"
 #include "tc_ptx.cuh"

@@ -87,7 +87,6 @@ struct TcLayer {
   void* d_weights = nullptr;         // packed [phase][Cout][K] K-major (bf16 or fp32/tf32)
   int k_total[4] = {0, 0, 0, 0};
   CUtensorMap tmap_b[4];             // per phase, 2-D [Cout][K]
-  CUtensorMap tmap_b_half[4];        // same with a 64-row box (cluster kernels load half an N tile each)
   // A-operand tensor map depends on (workspace, batch): cached for the last pair seen
   mutable CUtensorMap tmap_a;
   mutable const void* tmap_a_base = nullptr;
