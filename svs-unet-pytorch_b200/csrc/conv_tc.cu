@@ -526,9 +526,17 @@ int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
       int rc = encode_tensor_map(&t.tmap_b[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides, box,
                           t.swz);
       if (rc != SVS_OK) return rc;
+      t.tmap_b_wide[ph] = t.tmap_b[ph];
+      if (!t.merged && t.block_n == 128 && t.swz == 128 && n_total % 256 == 0) {
+        const cuuint32_t box_wide[2] = {static_cast<cuuint32_t>(t.block_k), 256u};
+        rc = encode_tensor_map(&t.tmap_b_wide[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides,
+                               box_wide, t.swz);
+        if (rc != SVS_OK) return rc;
+        t.has_wide = true;
+      }
       off += n;
     }
-    for (int ph = t.n_phases; ph < 4; ++ph) t.tmap_b[ph] = t.tmap_b[0];
+    for (int ph = t.n_phases; ph < 4; ++ph) { t.tmap_b[ph] = t.tmap_b[0]; t.tmap_b_wide[ph] = t.tmap_b_wide[0]; }
     SVS_CUDA_TRY(cudaStreamSynchronize(st));     // d_src / host vectors are consumed
     SVS_CUDA_TRY(cudaFree(d_src));
     t.enabled = true;
@@ -558,11 +566,13 @@ int tc_cluster_mode() {
 bool ck_supported(const svs_unet_plan* plan, int li, int split);
 int ck_launch_layer(const svs_unet_plan* plan, int li, const CUtensorMap& ta, const TcParams& p, cudaStream_t st);
 
-void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, int* split_k) {
+// Tiling of one layer at one batch size: M tiles, the N tile (a layer with has_wide may use 256) and split-K.
+void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, int* split_k, int* block_n) {
   const int ntw = t.gw / t.bw, nth = t.gh / t.bh, ntb = (batch + t.nb - 1) / t.nb;
   *m_tiles = ntw * nth * ntb;
-  const int n_tiles = (t.merged ? 4 * g.cout : g.cout) / t.block_n;
-  const int tiles = *m_tiles * n_tiles * t.n_phases;
+  *block_n = t.block_n;
+  const int n_total = t.merged ? 4 * g.cout : g.cout;
+  const int tiles = *m_tiles * (n_total / t.block_n) * t.n_phases;
   int min_chunks = 1 << 30;
   for (int ph = 0; ph < t.n_phases; ++ph) min_chunks = t.phases[ph].n_chunks < min_chunks ? t.phases[ph].n_chunks : min_chunks;
   int s = 1;
@@ -576,6 +586,15 @@ void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, in
   }
   if (s < 1 || t.merged) s = 1;
   *split_k = s;
+  // These layers are bound by L2 -> shared-memory bytes (~55 B/clk/SM): a 128 x 256 tile moves 48 KB per K chunk
+  // for twice the MACs of a 128 x 128 tile's 32 KB.  Worth it once the wider tiles still fill the SMs.
+  static const bool no_wide = [] { const char* w = std::getenv("SVS_TC_NO_WIDE"); return w && w[0] == '1'; }();
+  if (t.has_wide && s == 1 && !no_wide) {
+    const int sms = num_sms();
+    const int wide_tiles = *m_tiles * (n_total / 256) * t.n_phases;
+    const int cost_narrow = (tiles + sms - 1) / sms * 32, cost_wide = (wide_tiles + sms - 1) / sms * 48;
+    if (cost_wide < cost_narrow) *block_n = 256;
+  }
 }
 
 size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch) {
@@ -583,8 +602,8 @@ size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch) {
   for (int li = 0; li < 12; ++li) {
     const TcLayer& t = plan->tc[li];
     if (!t.enabled) continue;
-    int m_tiles, split;
-    tc_tiling(t, kLayers[li], batch, &m_tiles, &split);
+    int m_tiles, split, block_n;
+    tc_tiling(t, kLayers[li], batch, &m_tiles, &split, &block_n);
     if (split > 1) {
       const size_t bytes = static_cast<size_t>(split) * t.n_phases * m_tiles * 128 * kLayers[li].cout * sizeof(float);
       best = bytes > best ? bytes : best;
@@ -594,14 +613,14 @@ size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch) {
 }
 
 int tc_launch_count(const svs_unet_plan* plan, int li, int batch) {
-  int m_tiles, split;
-  tc_tiling(plan->tc[li], kLayers[li], batch, &m_tiles, &split);
+  int m_tiles, split, block_n;
+  tc_tiling(plan->tc[li], kLayers[li], batch, &m_tiles, &split, &block_n);
   if (split > 1 && tc_cluster_mode() == 2 && ck_supported(plan, li, split)) return 1;
   return split > 1 ? 2 : 1;   // main kernel (+ split-K reduction)
 }
 
 template <typename OutT, bool kTf32, int kBlockN, int kSwz, int kStages>
-static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p, int total_tiles, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap* tb, const TcParams& p, int total_tiles, cudaStream_t st) {
   auto kern = tc_conv_kernel<OutT, kTf32, kBlockN, kSwz, kStages>;
   constexpr size_t smem = tc_smem_bytes<kBlockN, kSwz, kStages>();
   SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -613,8 +632,7 @@ static int launch_tc(const CUtensorMap& ta, const TcLayer& t, const TcParams& p,
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > total_tiles) grid = total_tiles;
-  SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, st, ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2],
-                          t.tmap_b[3], p));
+  SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, st, ta, tb[0], tb[1], tb[2], tb[3], p));
   return SVS_OK;
 }
 
@@ -646,8 +664,9 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     p.py[ph] = t.phases[ph < t.n_phases ? ph : 0].py;
     p.px[ph] = t.phases[ph < t.n_phases ? ph : 0].px;
   }
-  int m_tiles, split;
-  tc_tiling(t, g, batch, &m_tiles, &split);
+  int m_tiles, split, block_n;
+  tc_tiling(t, g, batch, &m_tiles, &split, &block_n);
+  const CUtensorMap* tb = block_n == t.block_n ? t.tmap_b : t.tmap_b_wide;
   p.n_phases = t.n_phases;
   p.split_k = split;
   p.ntw = t.gw / t.bw; p.nth = t.gh / t.bh;
@@ -671,7 +690,7 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   if (split > 1 && ws.splitk_bytes < static_cast<size_t>(split) * t.n_phases * p.m_pad * g.cout * sizeof(float))
     return fail(SVS_ERR_WORKSPACE, "tc_launch_layer: split-K scratch too small");
   p.m_tiles = m_tiles;
-  p.n_tiles = p.cout / t.block_n;
+  p.n_tiles = p.cout / block_n;
   const int grid = m_tiles * p.n_tiles * t.n_phases * split;
   int rc = SVS_ERR_NOT_IMPLEMENTED;
   bool finish = split > 1;
@@ -680,9 +699,9 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     finish = false;
   }
 #define SVS_TC_CASE(N, S, ST)                                                                       \
-  if (rc == SVS_ERR_NOT_IMPLEMENTED && t.block_n == N && t.swz == S) { \
-    rc = tf32 ? launch_tc<float, true, N, S, ST>(ta, t, p, grid, st)                                \
-              : launch_tc<__nv_bfloat16, false, N, S, ST>(ta, t, p, grid, st);                      \
+  if (rc == SVS_ERR_NOT_IMPLEMENTED && block_n == N && t.swz == S) { \
+    rc = tf32 ? launch_tc<float, true, N, S, ST>(ta, tb, p, grid, st)                                \
+              : launch_tc<__nv_bfloat16, false, N, S, ST>(ta, tb, p, grid, st);                      \
   }
   SVS_TC_CASE(256, 128, 4)
   SVS_TC_CASE(128, 128, 6)
@@ -694,7 +713,7 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   SVS_TC_CASE(32, 32, 4)
 #undef SVS_TC_CASE
   if (rc == SVS_ERR_NOT_IMPLEMENTED)
-    return fail(rc, "tc_launch_layer: no kernel instantiation for block_n=" + std::to_string(t.block_n) +
+    return fail(rc, "tc_launch_layer: no kernel instantiation for block_n=" + std::to_string(block_n) +
                         " swz=" + std::to_string(t.swz));
   if (rc != SVS_OK) return rc;
   if (finish) {

@@ -87,6 +87,8 @@ struct TcLayer {
   void* d_weights = nullptr;         // packed [phase][Cout][K] K-major (bf16 or fp32/tf32)
   int k_total[4] = {0, 0, 0, 0};
   CUtensorMap tmap_b[4];             // per phase, 2-D [Cout][K]
+  bool has_wide = false;             // deep layers also carry a 256-row box: large batches use 128 x 256 tiles
+  CUtensorMap tmap_b_wide[4];
   // A-operand tensor map depends on (workspace, batch): cached for the last pair seen
   mutable CUtensorMap tmap_a;
   mutable const void* tmap_a_base = nullptr;

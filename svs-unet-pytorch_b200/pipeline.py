@@ -39,7 +39,7 @@ def patch_table(frames_per_song, frame_off):
 class Separator:
     """Runs whole songs through the fused path on one GPU."""
 
-    def __init__(self, model, max_batch: int = 64):
+    def __init__(self, model, max_batch: int = 512):
         self.model = model
         self.max_batch = int(max_batch)
 

@@ -13,12 +13,13 @@ def main():
     n_songs = int(sys.argv[1]) if len(sys.argv) > 1 else 150
     seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 180.0
     prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
+    max_batch = int(sys.argv[4]) if len(sys.argv) > 4 else 64
     n = int(seconds * 8192)
     torch.manual_seed(0)
     net = svs_model.UNet(precision=prec).eval().cuda()
     audio = torch.randn(n_songs * n, device="cuda") * 0.1
     batch = spectral.SongBatch(audio, [n] * n_songs)
-    sep = pipeline.Separator(net, max_batch=64)
+    sep = pipeline.Separator(net, max_batch=max_batch)
     for _ in range(2):
         wave, peak = sep.separate_batch(batch)
     torch.cuda.synchronize()
@@ -33,7 +34,7 @@ def main():
     ms = e0.elapsed_time(e1) / reps
     wall = (time.perf_counter() - t0) / reps * 1e3
     patches = n_songs * (batch.frames[0] // 128 + 1)
-    print(f"{n_songs} songs x {seconds:.0f}s ({patches} patches, {batch.total_frames} frames) [{prec}]: {ms:.2f} ms device "
+    print(f"{n_songs} songs x {seconds:.0f}s ({patches} patches, {batch.total_frames} frames) [{prec}, max_batch {max_batch}]: {ms:.2f} ms device "
           f"({wall:.2f} ms wall) -> {n_songs * seconds / ms * 1e3:.3e} audio-s/s, {patches / ms * 1e3:.0f} patches/s")
 
 
