@@ -106,6 +106,21 @@ int svs_istft_ola(const float* mag, const float* phase, const int64_t* frame_off
 int svs_wave_peak_normalize(float* wave, const int64_t* wave_off, const float* song_peak,
                             int n_songs, int64_t total_samples, float target, void* stream);
 
+/* ------------------------------------------------------------------ patch staging (I2, I4)
+ * Replaces the per-patch segment / zero-pad / contiguous copy of reference inference.py:74-97 and the
+ * crop / concatenate / DC re-insert of inference.py:110-127, for `n` patches at once.
+ *   spec        frame-major song spectrogram(s) [frames][513] float32
+ *   patch_off   device [n] element offsets of each patch's first element (frame * 513 + 1: DC bin skipped)
+ *   in_frames   device [n] valid frames per patch (<= 128), or NULL for 128
+ *   patches     dense [n][512][128] float32
+ * gather: patches[p][f][t] = spec[patch_off[p] + t*513 + f] / norm[p] for t < in_frames[p], else 0; `norm` (device
+ * [n], NULL = 1) folds the per-song normalisation of data.py:85,105 (0 -> 1) into the copy.
+ * scatter: the inverse for t < in_frames[p]; dc_zero != 0 also writes 0 to the DC bin of those frames. */
+int svs_patches_gather(const float* spec, const int64_t* patch_off, const int32_t* in_frames,
+                       const float* norm, float* patches, int n, void* stream);
+int svs_patches_scatter(const float* patches, const int64_t* patch_off, const int32_t* in_frames,
+                        float* spec, int n, int dc_zero, void* stream);
+
 /* ------------------------------------------------------------------ UNet mask (U1-D6, I2-I4)
  * Replaces UNet.forward (reference model.py:169-201) in eval mode followed by the mask
  * application of reference inference.py:102,107.

@@ -56,6 +56,8 @@ _SIGNATURES = [
     ("svs_spec_normalize", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     ("svs_istft_ola", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     ("svs_wave_peak_normalize", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p]),
+    ("svs_patches_gather", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ("svs_patches_scatter", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     ("svs_unet_plan_create", c_int, [POINTER(ConvParams), c_int, c_void_p, POINTER(c_void_p)]),
     ("svs_unet_plan_destroy", c_int, [c_void_p]),
     ("svs_unet_plan_precision", c_int, [c_void_p]),
@@ -203,6 +205,33 @@ def wave_peak_normalize_raw(wave, wave_off, peak, n_songs, target=0.9):
                                              wave.numel(), target, stream_ptr(wave.device)),
               "svs_wave_peak_normalize")
     return wave
+
+
+def patches_gather_raw(spec, patch_off, in_frames, norm, out=None):
+    """Frame-major spectrogram [frames][513] -> dense patches [n][1][512][128] (reference inference.py:74-97), with
+    the per-patch norm (data.py:85,105) folded in when given."""
+    require_cuda(spec, "spec", torch.float32)
+    n = int(patch_off.numel())
+    if out is None:
+        out = torch.empty((n, 1, 512, 128), dtype=torch.float32, device=spec.device)
+    with torch.cuda.device(spec.device):
+        check(load().svs_patches_gather(spec.data_ptr(), patch_off.data_ptr(),
+                                        in_frames.data_ptr() if in_frames is not None else None,
+                                        norm.data_ptr() if norm is not None else None, out.data_ptr(), n,
+                                        stream_ptr(spec.device)), "svs_patches_gather")
+    return out
+
+
+def patches_scatter_raw(patches, patch_off, in_frames, spec, dc_zero=True):
+    """Dense patches -> frame-major spectrogram (crop + concatenate + DC row of reference inference.py:110-127)."""
+    require_cuda(patches, "patches", torch.float32)
+    require_cuda(spec, "spec", torch.float32)
+    n = int(patch_off.numel())
+    with torch.cuda.device(spec.device):
+        check(load().svs_patches_scatter(patches.data_ptr(), patch_off.data_ptr(),
+                                         in_frames.data_ptr() if in_frames is not None else None, spec.data_ptr(), n,
+                                         1 if dc_zero else 0, stream_ptr(spec.device)), "svs_patches_scatter")
+    return spec
 
 
 # ---------------------------------------------------------------------------------------------

@@ -8,8 +8,9 @@ HBM.  The patch logic restates reference inference.py:65-127:
 * the time axis is cut into 128-frame patches, ``T // 128 + 1`` of them with the empty one skipped,
 * the last patch is zero padded (frames >= valid are read as 0 by conv1) and cropped (not written).
 
-Nothing is copied to build patches: the UNet kernels read / write the frame-major spectrogram
-([T][513], i.e. librosa's Fortran-ordered (513, T)) through a strided patch view.
+Patches are staged by a tiled transpose at HBM speed (svs_patches_gather / svs_patches_scatter, with the
+normalisation folded into the gather); with ``staged=False`` the UNet kernels instead read / write the
+frame-major spectrogram ([T][513], i.e. librosa's Fortran-ordered (513, T)) through a strided patch view.
 """
 from __future__ import annotations
 
@@ -39,9 +40,10 @@ def patch_table(frames_per_song, frame_off):
 class Separator:
     """Runs whole songs through the fused path on one GPU."""
 
-    def __init__(self, model, max_batch: int = 512):
+    def __init__(self, model, max_batch: int = 512, staged: bool = True):
         self.model = model
         self.max_batch = int(max_batch)
+        self.staged = bool(staged)      # False: the UNet reads / writes the spectrogram through strided patch views
 
     @torch.no_grad()
     def separate_batch(self, batch: SongBatch, vocal_solo: bool = True, peak_normalize: bool = True,
@@ -50,19 +52,35 @@ class Separator:
         normalised mixture spectrogram, the phase and the masked spectrogram ([F,513] layouts)."""
         plan = self.model.plan()
         mag, phase, smax = batch.stft()
-        batch.normalize(mag, smax)                                    # data.py:105
-        offs, valid, _ = patch_table(batch.frames, batch.frame_off_host)
+        offs, valid, song = patch_table(batch.frames, batch.frame_off_host)
         dev = mag.device
         d_off = torch.from_numpy(offs).to(dev)
         d_valid = torch.from_numpy(valid).to(dev)
-        out_mag = torch.zeros_like(mag)                               # DC row stays 0 (inference.py:123)
         flags = _lib.FLAG_APPLY_MASK | (0 if vocal_solo else _lib.FLAG_INVERT)
         n = len(offs)
-        for a in range(0, n, self.max_batch):
-            b = min(n, a + self.max_batch)
-            iv = _lib.PatchView(mag.data_ptr(), d_off[a:b].data_ptr(), 0, 1, N_BINS)
-            ov = _lib.PatchView(out_mag.data_ptr(), d_off[a:b].data_ptr(), 0, 1, N_BINS)
-            plan.forward_views(iv, ov, d_valid[a:b], b - a, flags)
+        if self.staged:
+            # gather -> dense UNet batches -> scatter: conv1 and deconv6 stay on their TMA / tensor-core paths, and
+            # every frame row of out_mag is written in full.  Unless the caller wants the normalised spectrogram
+            # back, the data.py:105 normalisation is folded into the gather instead of a pass of its own.
+            d_norm = None
+            if return_spec:
+                batch.normalize(mag, smax)
+            else:
+                d_norm = smax[torch.from_numpy(song).to(dev).long()]
+            out_mag = torch.empty_like(mag)
+            for a in range(0, n, self.max_batch):
+                b = min(n, a + self.max_batch)
+                x = _lib.patches_gather_raw(mag, d_off[a:b], d_valid[a:b], None if d_norm is None else d_norm[a:b])
+                y = plan.forward_dense(x, flags)
+                _lib.patches_scatter_raw(y, d_off[a:b], d_valid[a:b], out_mag, dc_zero=True)
+        else:
+            batch.normalize(mag, smax)                                # data.py:105
+            out_mag = torch.zeros_like(mag)                           # DC row stays 0 (inference.py:123)
+            for a in range(0, n, self.max_batch):
+                b = min(n, a + self.max_batch)
+                iv = _lib.PatchView(mag.data_ptr(), d_off[a:b].data_ptr(), 0, 1, N_BINS)
+                ov = _lib.PatchView(out_mag.data_ptr(), d_off[a:b].data_ptr(), 0, 1, N_BINS)
+                plan.forward_views(iv, ov, d_valid[a:b], b - a, flags)
         wave, peak = batch.istft(out_mag, phase, peak_normalize=peak_normalize)   # data.py:159-164
         if return_spec:
             return wave, peak, mag, phase, out_mag

@@ -25,14 +25,15 @@ def test_patch_table_matches_reference_segmentation():
     assert offs[0] == 1 and offs[1] == 128 * 513 + 1 and offs[3] == 321 * 513 + 1
 
 
+@pytest.mark.parametrize("staged", [True, False])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2), ("tf32", 1e-3)])
-def test_full_song_round_trip_matches_oracle(precision, tol):
+def test_full_song_round_trip_matches_oracle(precision, tol, staged):
     # BASELINE configs[0] (30 s) + a ragged second song, both vocal_solo settings
     songs = [synth.synth_song(30.0, seed=1234), synth.synth_song(13.7, seed=99)]
     torch.manual_seed(0)
     net = svs_model.UNet(precision=precision).eval().cuda()
     sd = {k: v.cpu() for k, v in net.state_dict().items()}
-    sep = pipeline.Separator(net, max_batch=4)
+    sep = pipeline.Separator(net, max_batch=4, staged=staged)
     for vocal_solo in (True, False):
         batch = spectral.SongBatch.from_audio([s[0] for s in songs])
         wave, peak, mag, phase, out_mag = sep.separate_batch(batch, vocal_solo=vocal_solo, return_spec=True)
@@ -48,6 +49,49 @@ def test_full_song_round_trip_matches_oracle(precision, tol):
             target = voc if vocal_solo else acc
             d = abs(synth.sdr_db(target, y) - synth.sdr_db(target, y_ref))
             assert d <= 0.05, d                                       # north_star: within 0.05 dB SDR
+
+
+def test_patch_staging_matches_indexing():
+    # svs_patches_gather / svs_patches_scatter against plain indexing (reference inference.py:74-97, 110-127)
+    from svs_unet_pytorch_b200 import _lib
+    frames = [321, 128, 1, 200]
+    frame_off = np.concatenate([[0], np.cumsum(frames)])
+    offs, valid, song = pipeline.patch_table(frames, frame_off)
+    g = torch.Generator().manual_seed(3)
+    spec = torch.rand(int(frame_off[-1]), 513, generator=g).cuda()
+    norm = torch.tensor([2.0, 0.0, 0.5, 3.0], device="cuda")[torch.from_numpy(song).cuda().long()]   # 0 -> 1
+    d_off, d_valid = torch.from_numpy(offs).cuda(), torch.from_numpy(valid).cuda()
+    patches = _lib.patches_gather_raw(spec, d_off, d_valid, norm)
+    assert patches.shape == (len(offs), 1, 512, 128)
+    for p in range(len(offs)):
+        f0 = (int(offs[p]) - 1) // 513
+        nrm = float(norm[p]) or 1.0
+        ref = torch.zeros(512, 128, device="cuda")
+        blk = spec[f0: f0 + valid[p], 1:]
+        ref[:, : valid[p]] = torch.div(blk, torch.full_like(blk, nrm)).T      # true division, as data.py:85
+        assert torch.equal(patches[p, 0], ref), p
+    out = torch.full_like(spec, -1.0)
+    _lib.patches_scatter_raw(patches, d_off, d_valid, out, dc_zero=True)
+    assert torch.all(out[:, 0] == 0)
+    for p in range(len(offs)):
+        f0 = (int(offs[p]) - 1) // 513
+        assert torch.equal(out[f0: f0 + valid[p], 1:], patches[p, 0, :, : valid[p]].T)
+    assert not torch.any(out == -1.0)                                  # every frame row written in full
+    same = _lib.patches_gather_raw(spec, d_off[:1], None, None)        # NULL in_frames / norm: a full, unscaled patch
+    assert torch.equal(same[0, 0], spec[:128, 1:].T)
+
+
+def test_staged_and_view_paths_agree_on_a_corpus_slice():
+    songs = [synth.synth_song(20.0, seed=5)[0], synth.synth_song(31.0, seed=6)[0]]
+    torch.manual_seed(0)
+    net = svs_model.UNet(precision="bf16").eval().cuda()
+    waves = []
+    for staged in (True, False):
+        sep = pipeline.Separator(net, max_batch=3, staged=staged)
+        waves.append(sep.separate(songs))
+    for a, b in zip(*waves):
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= 2e-2 * 0.9                       # conv1 differs (tensor-core vs CUDA-core path)
 
 
 def test_host_streamer_matches_direct_forward():
