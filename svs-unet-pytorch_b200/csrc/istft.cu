@@ -137,18 +137,29 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   }
 }
 
-__global__ void wave_peak_normalize_kernel(float* __restrict__ wave, const int64_t* __restrict__ wave_off,
-                                           const float* __restrict__ song_peak, int n_songs,
-                                           int64_t total, float target) {
+// grid (blocks per song, n_songs): no per-element song lookup, 16-byte accesses (song offsets are multiples of the
+// 768-sample hop, so a song starts 16-byte aligned whenever the buffer does)
+__global__ void __launch_bounds__(256)
+wave_peak_normalize_kernel(float* __restrict__ wave, const int64_t* __restrict__ wave_off,
+                           const float* __restrict__ song_peak, float target) {
+  const int s = blockIdx.y;
+  const float pk = song_peak[s];
+  if (!(pk > 0.0f)) return;                                  // reference data.py:163: silent songs stay as they are
+  const int64_t a = wave_off[s], n = wave_off[s + 1] - a;
+  float* w = wave + a;
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int lo = 0, hi = n_songs - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (wave_off[mid] <= i) lo = mid; else hi = mid - 1;
+  if ((reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    float4* w4 = reinterpret_cast<float4*>(w);
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 v = w4[i];
+      v.x = v.x / pk * target; v.y = v.y / pk * target; v.z = v.z / pk * target; v.w = v.w / pk * target;   // data.py:164
+      w4[i] = v;
     }
-    const float pk = song_peak[lo];
-    if (pk > 0.0f) wave[i] = wave[i] / pk * target;          // reference data.py:163-164
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) w[i] = w[i] / pk * target;
+  } else {
+    for (int64_t i = tid; i < n; i += stride) w[i] = w[i] / pk * target;
   }
 }
 
@@ -180,12 +191,13 @@ extern "C" int svs_wave_peak_normalize(float* wave, const int64_t* wave_off, con
                                        int n_songs, int64_t total_samples, float target, void* stream) {
   using namespace svs;
   SVS_REQUIRE(wave && wave_off && song_peak, "svs_wave_peak_normalize: null pointer");
-  SVS_REQUIRE(n_songs > 0 && total_samples >= 0, "svs_wave_peak_normalize: bad sizes");
+  SVS_REQUIRE(n_songs > 0 && n_songs <= 65535 && total_samples >= 0, "svs_wave_peak_normalize: bad sizes");
   if (total_samples == 0) return SVS_OK;
-  int64_t blocks = (total_samples + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  wave_peak_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      wave, wave_off, song_peak, n_songs, total_samples, target);
+  // enough CTAs to fill the GPU for a single song, fewer per song when there are many
+  int per_song = (148 * 8 + n_songs - 1) / n_songs;
+  if (per_song < 4) per_song = 4;
+  wave_peak_normalize_kernel<<<dim3(per_song, n_songs), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      wave, wave_off, song_peak, target);
   SVS_CHECK_LAUNCH("wave_peak_normalize_kernel");
   return SVS_OK;
 }

@@ -44,6 +44,18 @@ class Separator:
         self.model = model
         self.max_batch = int(max_batch)
         self.staged = bool(staged)      # False: the UNet reads / writes the spectrogram through strided patch views
+        self._table_key, self._table_val = None, None
+
+    def _table(self, batch: SongBatch, dev):
+        """Patch table of a song batch on the device; cached for the last batch geometry (a corpus of equal-length
+        songs re-uses it, and building it costs a host loop plus three small H2D copies while the GPU idles)."""
+        key = (tuple(batch.frames), str(dev))
+        if key != self._table_key:
+            offs, valid, song = patch_table(batch.frames, batch.frame_off_host)
+            self._table_val = (offs, torch.from_numpy(offs).to(dev), torch.from_numpy(valid).to(dev),
+                               torch.from_numpy(song).to(dev).long())
+            self._table_key = key
+        return self._table_val
 
     @torch.no_grad()
     def separate_batch(self, batch: SongBatch, vocal_solo: bool = True, peak_normalize: bool = True,
@@ -52,10 +64,8 @@ class Separator:
         normalised mixture spectrogram, the phase and the masked spectrogram ([F,513] layouts)."""
         plan = self.model.plan()
         mag, phase, smax = batch.stft()
-        offs, valid, song = patch_table(batch.frames, batch.frame_off_host)
         dev = mag.device
-        d_off = torch.from_numpy(offs).to(dev)
-        d_valid = torch.from_numpy(valid).to(dev)
+        offs, d_off, d_valid, d_song = self._table(batch, dev)
         flags = _lib.FLAG_APPLY_MASK | (0 if vocal_solo else _lib.FLAG_INVERT)
         n = len(offs)
         if self.staged:
@@ -66,7 +76,7 @@ class Separator:
             if return_spec:
                 batch.normalize(mag, smax)
             else:
-                d_norm = smax[torch.from_numpy(song).to(dev).long()]
+                d_norm = smax[d_song]
             out_mag = torch.empty_like(mag)
             for a in range(0, n, self.max_batch):
                 b = min(n, a + self.max_batch)
