@@ -31,7 +31,33 @@ constexpr size_t d6_smem_bytes() {
   return (operands > p ? operands : p) + 1024 + 64;
 }
 
-template <bool kTf32, int kSwz>
+// col2im for one PAIR of adjacent outputs (2n, 2n+1) of output row 2m+PY: the five kw taps of a kernel row share
+// one base address (lane = n: conflict-free), PY fixes kh, so every tap offset is a compile-time constant.
+template <int PY>
+__device__ __forceinline__ float2 d6_gather_pair(const float* __restrict__ P, int mr, int n, float bs) {
+  float a0 = bs, a1 = bs;
+  const bool lo = n > 0, hi = n < 63;                                  // columns n-1 / n+1 exist
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int kh = PY + 2 * a;
+    if (kh > 4) continue;
+    const float* row = P + (mr + ((PY + 2 - kh) >> 1)) * 64 + n;       // halo rows are zero-filled by TMA
+    // px = 0: kw = 0, 2, 4 -> columns n+1, n, n-1;  px = 1: kw = 1, 3 -> columns n+1, n
+    const float t0 = hi ? row[(kh * 5 + 0) * kD6PPitch + 1] : 0.0f;
+    const float t2 = row[(kh * 5 + 2) * kD6PPitch];
+    const float t4 = lo ? row[(kh * 5 + 4) * kD6PPitch - 1] : 0.0f;
+    const float t1 = hi ? row[(kh * 5 + 1) * kD6PPitch + 1] : 0.0f;
+    const float t3 = row[(kh * 5 + 3) * kD6PPitch];
+    a0 += t0; a0 += t2; a0 += t4;
+    a1 += t1; a1 += t3;
+  }
+  return make_float2(a0, a1);
+}
+
+// kDense: mixture and output are contiguous [B][512][128] float32 (the staged pipeline and the dense UNet entry):
+// 32-bit index math, 8-byte mixture loads and stores, a thread owns output pairs.  Otherwise the generic strided
+// patch view (one output per thread step, 64-bit strides).
+template <bool kTf32, int kSwz, bool kDense>
 __global__ void __launch_bounds__(kD6Threads)
 deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const float* __restrict__ bias, const float* __restrict__ mix,
@@ -88,16 +114,30 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   // ---- prefetch the mixture values this thread will need in the gather (independent of the GEMM), so
   //      their DRAM latency hides behind TMA + MMA + drain instead of serialising inside the gather loop
   constexpr int kOutPerThread = 2 * kD6Interior * 128 / kD6Threads;     // 6
+  constexpr int kPairsPerThread = kOutPerThread / 2;                    // 3
   const int nf = in_frames ? in_frames[b] : SVS_PATCH_FRAMES;
   const float* mix_b = mix + (mix_off ? mix_off[b] : b * mix_sb);
   float mixv[kOutPerThread];
+  if constexpr (kDense) {
+    // pair pr = threadIdx.x + 256 j: n = pr & 63, output row (local) = pr >> 6
 #pragma unroll
-  for (int j = 0; j < kOutPerThread; ++j) {
-    const int o = threadIdx.x + j * kD6Threads;
-    const int ox = o & 127, oyl = o >> 7;
-    const int m = row0 + 1 + (oyl >> 1);
-    const int oy = 2 * m + (oyl & 1);
-    mixv[j] = ((flags & SVS_FLAG_APPLY_MASK) && m < 256 && ox < nf) ? __ldg(mix_b + oy * mix_sf + ox * mix_st) : 1.0f;
+    for (int j = 0; j < kPairsPerThread; ++j) {
+      const int pr = threadIdx.x + j * kD6Threads;
+      const int n = pr & 63, oyl = pr >> 6;
+      const int oy = 2 * (row0 + 1 + (oyl >> 1)) + (oyl & 1);
+      float2 v = make_float2(1.0f, 1.0f);
+      if ((flags & SVS_FLAG_APPLY_MASK) && oy < 512) v = __ldg(reinterpret_cast<const float2*>(mix_b + oy * 128 + 2 * n));
+      mixv[2 * j] = v.x; mixv[2 * j + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kOutPerThread; ++j) {
+      const int o = threadIdx.x + j * kD6Threads;
+      const int ox = o & 127, oyl = o >> 7;
+      const int m = row0 + 1 + (oyl >> 1);
+      const int oy = 2 * m + (oyl & 1);
+      mixv[j] = ((flags & SVS_FLAG_APPLY_MASK) && m < 256 && ox < nf) ? __ldg(mix_b + oy * mix_sf + ox * mix_st) : 1.0f;
+    }
   }
   if (warp == 0) {
     mbar_wait(bar_full, 0);
@@ -140,33 +180,52 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   // ---- col2im gather + sigmoid + mask: 12 output rows x 128 frames ----
   const float bs = __ldg(bias);
   float* out_b = out + (out_off ? out_off[b] : b * out_sb);
+  if constexpr (kDense) {
 #pragma unroll
-  for (int j = 0; j < kOutPerThread; ++j) {
-    const int o = threadIdx.x + j * kD6Threads;
-    const int ox = o & 127, oyl = o >> 7;
-    const int mr = 1 + (oyl >> 1);                                     // slab row of the input pixel
-    const int m = row0 + mr;                                           // global input row
-    if (m >= 256 || ox >= nf) continue;
-    const int py = oyl & 1, px = ox & 1, n = ox >> 1;
-    float acc = bs;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int kh = py + 2 * a;
-      if (kh > 4) continue;
-      const int rr = mr + ((py + 2 - kh) >> 1);                        // slab row (halo rows are zero-filled by TMA)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int kw = px + 2 * c;
-        if (kw > 4) continue;
-        const int cc = n + ((px + 2 - kw) >> 1);
-        if (cc < 0 || cc >= 64) continue;
-        acc += P[(kh * 5 + kw) * kD6PPitch + rr * 64 + cc];
-      }
+    for (int j = 0; j < kPairsPerThread; ++j) {
+      const int pr = threadIdx.x + j * kD6Threads;
+      const int n = pr & 63, oyl = pr >> 6;                            // oyl parity is warp-uniform
+      const int mr = 1 + (oyl >> 1);
+      const int oy = 2 * (row0 + mr) + (oyl & 1);
+      if (oy >= 512) continue;
+      const float2 acc = (oyl & 1) ? d6_gather_pair<1>(P, mr, n, bs) : d6_gather_pair<0>(P, mr, n, bs);
+      float m0 = __fdividef(1.0f, 1.0f + __expf(-acc.x));              // torch.sigmoid, model.py:200
+      float m1 = __fdividef(1.0f, 1.0f + __expf(-acc.y));
+      if (flags & SVS_FLAG_INVERT) { m0 = 1.0f - m0; m1 = 1.0f - m1; } // inference.py:102
+      float* dst = out_b + oy * 128 + 2 * n;
+      // inference.py:107 (mixv = 1 without APPLY_MASK); frames >= nf are cropped (inference.py:113)
+      if (2 * n + 1 < nf) *reinterpret_cast<float2*>(dst) = make_float2(m0 * mixv[2 * j], m1 * mixv[2 * j + 1]);
+      else if (2 * n < nf) dst[0] = m0 * mixv[2 * j];
     }
-    float mval = 1.0f / (1.0f + __expf(-acc));                         // torch.sigmoid, model.py:200
-    if (flags & SVS_FLAG_INVERT) mval = 1.0f - mval;                   // inference.py:102
-    const int oy = 2 * m + py;
-    out_b[oy * out_sf + ox * out_st] = mval * mixv[j];                 // inference.py:107 (mixv = 1 without APPLY_MASK)
+  } else {
+#pragma unroll
+    for (int j = 0; j < kOutPerThread; ++j) {
+      const int o = threadIdx.x + j * kD6Threads;
+      const int ox = o & 127, oyl = o >> 7;
+      const int mr = 1 + (oyl >> 1);                                     // slab row of the input pixel
+      const int m = row0 + mr;                                           // global input row
+      if (m >= 256 || ox >= nf) continue;
+      const int py = oyl & 1, px = ox & 1, n = ox >> 1;
+      float acc = bs;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const int kh = py + 2 * a;
+        if (kh > 4) continue;
+        const int rr = mr + ((py + 2 - kh) >> 1);                        // slab row (halo rows are zero-filled by TMA)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int kw = px + 2 * c;
+          if (kw > 4) continue;
+          const int cc = n + ((px + 2 - kw) >> 1);
+          if (cc < 0 || cc >= 64) continue;
+          acc += P[(kh * 5 + kw) * kD6PPitch + rr * 64 + cc];
+        }
+      }
+      float mval = 1.0f / (1.0f + __expf(-acc));                         // torch.sigmoid, model.py:200
+      if (flags & SVS_FLAG_INVERT) mval = 1.0f - mval;                   // inference.py:102
+      const int oy = 2 * m + py;
+      out_b[oy * out_sf + ox * out_st] = mval * mixv[j];                 // inference.py:107 (mixv = 1 without APPLY_MASK)
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -220,24 +279,24 @@ int d6_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_vi
   int rc = encode_tensor_map(&ta, tf32, 4, ws.buf[BUF_CAT1], dims, strides, box, 32 * es);
   if (rc != SVS_OK) return rc;
   dim3 grid((256 + kD6Interior - 1) / kD6Interior, batch);
-  if (tf32) {
-    constexpr size_t smem = d6_smem_bytes<128>();
-    SVS_CUDA_TRY(cudaFuncSetAttribute(deconv6_tc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-    SVS_CUDA_TRY(launch_pdl(deconv6_tc_kernel<true, 128>, grid, dim3(kD6Threads), smem, st, ta, plan->d6_tmap_w,
+  auto dense_view = [](const svs_patch_view* v) {
+    return v->patch_off == nullptr && v->stride_t == 1 && v->stride_f == SVS_PATCH_FRAMES &&
+           v->stride_b == static_cast<int64_t>(SVS_PATCH_BINS) * SVS_PATCH_FRAMES &&
+           (reinterpret_cast<uintptr_t>(v->base) & 7) == 0;
+  };
+  const bool dense = dense_view(in) && dense_view(out);
+  auto launch = [&](auto kern, size_t smem) -> int {
+    SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SVS_CUDA_TRY(launch_pdl(kern, grid, dim3(kD6Threads), smem, st, ta, plan->d6_tmap_w,
                             static_cast<const float*>(plan->b_fold[11]), static_cast<const float*>(in->base),
                             in->patch_off, in->stride_b, in->stride_f, in->stride_t, out->base, out->patch_off,
                             out->stride_b, out->stride_f, out->stride_t, in_frames, flags));
-  } else {
-    constexpr size_t smem = d6_smem_bytes<64>();
-    SVS_CUDA_TRY(cudaFuncSetAttribute(deconv6_tc_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-    SVS_CUDA_TRY(launch_pdl(deconv6_tc_kernel<false, 64>, grid, dim3(kD6Threads), smem, st, ta, plan->d6_tmap_w,
-                            static_cast<const float*>(plan->b_fold[11]), static_cast<const float*>(in->base),
-                            in->patch_off, in->stride_b, in->stride_f, in->stride_t, out->base, out->patch_off,
-                            out->stride_b, out->stride_f, out->stride_t, in_frames, flags));
-  }
-  return SVS_OK;
+    return SVS_OK;
+  };
+  if (tf32) return dense ? launch(deconv6_tc_kernel<true, 128, true>, d6_smem_bytes<128>())
+                         : launch(deconv6_tc_kernel<true, 128, false>, d6_smem_bytes<128>());
+  return dense ? launch(deconv6_tc_kernel<false, 64, true>, d6_smem_bytes<64>())
+               : launch(deconv6_tc_kernel<false, 64, false>, d6_smem_bytes<64>());
 }
 
 }  // namespace svs
