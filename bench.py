@@ -253,7 +253,7 @@ def run_ours(args):
     ga = torch.Generator(device=dev).manual_seed(99 + rank)
     audio = torch.randn(len(mine) * n_samp, device=dev, generator=ga) * 0.1
     sbatch = spectral.SongBatch(audio, [n_samp] * len(mine))
-    sep = pipeline.Separator(net, max_batch=BATCH)
+    sep = pipeline.Separator(net)                                     # 512-patch UNet batches, staged patches
     for _ in range(2):
         sep.separate_batch(sbatch)
     barrier()
@@ -343,7 +343,8 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
                          "traffic_note": "dram read+write bytes summed over the 10 conv2..deconv5 launches of one 64-patch forward (ncu --set full, cold L2); algorithmic activation bytes: 2 x 64 x 0.98 M bf16 elements = 251 MB + 41 MB weights",
-                         "kernel": "zc_conv_kernel + tc_conv_kernel (tcgen05 implicit GEMM, conv2..deconv5; 10 layers, 13 launches)",
+                         "kernel": "zc_conv_kernel + tc_conv_kernel + tc_conv_ck_kernel (tcgen05 implicit GEMM, conv2..deconv5; "
+                                   f"10 layers, {plan.launch_count(BATCH) - 2} launches)",
                          "ms_per_step": ms_tc,
                          "peak_source": peaks["source"] + " bf16_tflops_sustained",
                          "flops": "exact valid-tap count of the layers the kernel executes"},
@@ -351,7 +352,8 @@ def run_ours(args):
             "pipeline": {"workload": "150 synthetic 3-min songs (BASELINE configs[3]) sharded by song, device resident: "
                                      "STFT -> /max -> UNet mask x mixture -> iSTFT -> 0.9 peak",
                          "audio_sec_per_sec": corpus * seconds / (ms_pipe * 1e-3), "ms_per_corpus": ms_pipe,
-                         "patches_per_sec": corpus * 16 / (ms_pipe * 1e-3)},
+                         "patches_per_sec": corpus * 16 / (ms_pipe * 1e-3),
+                         "unet_batch": sep.max_batch, "patch_staging": "svs_patches_gather / svs_patches_scatter"},
             "tflops_exact_whole_net": value * GFLOP_EXACT_PER_PATCH / 1e3,
             "tf32": None if ms_tf32 is None else {"patches_per_sec_per_gpu": BATCH / (ms_tf32 * 1e-3), "ms_per_step": ms_tf32,
                                                   "note": "same workload on the kind::tf32 path, direct launches (no graph), rank 0"},

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libsvs_b200.so")
-SOURCES = ["common.cu", "stft.cu", "istft.cu", "patches.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc_cluster.cu", "conv1_tc.cu", "zc_conv.cu", "deconv6_tc.cu", "unet.cu", "train.cu"]
+SOURCES = ["common.cu", "stft.cu", "istft.cu", "patches.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc_cluster.cu", "conv1_tc.cu", "conv1_zc.cu", "zc_conv.cu", "deconv6_tc.cu", "unet.cu", "train.cu"]
 
 
 def _nvcc() -> str:

@@ -38,13 +38,6 @@ constexpr size_t tc_smem_bytes() {
 }
 
 
-template <int S, int N, typename F>
-__device__ __forceinline__ void dispatch_stage(int s, F&& f) {
-  if constexpr (S < N) {
-    if (s == S) f(std::integral_constant<int, S>{});
-    else dispatch_stage<S + 1, N>(s, f);
-  }
-}
 
 // Persistent kernel: each CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is
 // double buffered in TMEM so the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.

@@ -31,13 +31,6 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int S, int N, typename F>
-__device__ __forceinline__ void dispatch_stage_ck(int s, F&& f) {
-  if constexpr (S < N) {
-    if (s == S) f(std::integral_constant<int, S>{});
-    else dispatch_stage_ck<S + 1, N>(s, f);
-  }
-}
 
 constexpr int kCkBlockN = 128;
 constexpr int kCkStages = 6;
@@ -153,7 +146,7 @@ tc_conv_ck_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (dbg && it == 0 && lane == 0) dbg[2] = dbg_now();
       tc_fence_after();
       const uint32_t acc0 = it > 0 ? 1u : 0u;
-      dispatch_stage_ck<0, kStages>(s, [&](auto sc) {
+      dispatch_stage<0, kStages>(s, [&](auto sc) {
         constexpr int S = decltype(sc)::value;
         const uint32_t a_addr = smem_base + S * kStageBytes;
         const uint64_t da = make_smem_desc<kSwz>(a_addr);

@@ -4,6 +4,8 @@
 #include "unet_internal.cuh"
 #include "tc_ptx.cuh"
 
+#include <type_traits>
+
 namespace svs {
 
 constexpr int kTcThreads = 192;
@@ -36,6 +38,16 @@ __device__ __forceinline__ long long dbg_now() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// Runs f(integral_constant<S>) for the runtime stage index s: inside, shared-memory descriptors are "uniform base +
+// compile-time constant", so tcgen05.mma issues without per-MMA descriptor arithmetic in the vector datapath.
+template <int S, int N, typename F>
+__device__ __forceinline__ void dispatch_stage(int s, F&& f) {
+  if constexpr (S < N) {
+    if (s == S) f(std::integral_constant<int, S>{});
+    else dispatch_stage<S + 1, N>(s, f);
+  }
+}
+
 __device__ __forceinline__ float tc_act(float v, int act) {
   if (act == ACT_LEAKY) return v > 0.0f ? v : 0.2f * v;
   if (act == ACT_RELU) return fmaxf(v, 0.0f);

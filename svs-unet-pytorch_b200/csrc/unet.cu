@@ -26,6 +26,9 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
 int tc_launch_count(const svs_unet_plan* plan, int li, int batch);
 // conv1_tc.cu
 int c1t_plan(svs_unet_plan* plan, cudaStream_t st);
+int c1z_plan(svs_unet_plan* plan, cudaStream_t st);
+void c1z_free(svs_unet_plan* plan);
+int c1z_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_view* in, int batch, cudaStream_t st);
 void c1t_free(svs_unet_plan* plan);
 bool c1t_applicable(const svs_patch_view* in, const int32_t* in_frames);
 int c1t_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_view* in, int batch, cudaStream_t st);
@@ -107,6 +110,8 @@ extern "C" int svs_unet_plan_create(const svs_conv_params layers[12], int precis
     if (!(dis && (std::strtoul(dis, nullptr, 0) & 1u))) {
       rc = c1t_plan(plan, st);
       if (rc != SVS_OK) { svs_unet_plan_destroy(plan); return rc; }
+      rc = c1z_plan(plan, st);
+      if (rc != SVS_OK) { svs_unet_plan_destroy(plan); return rc; }
     }
     if (!(dis && ((std::strtoul(dis, nullptr, 0) >> 11) & 1u))) {
       rc = d6_plan(plan, st);
@@ -122,6 +127,7 @@ extern "C" int svs_unet_plan_destroy(svs_unet_plan* plan) {
   tc_free_layers(plan);
   zc_free_layers(plan);
   c1t_free(plan);
+  c1z_free(plan);
   d6_free(plan);
   for (int i = 0; i < 12; ++i) {
     if (plan->w_fold[i]) cudaFree(plan->w_fold[i]);
@@ -163,7 +169,8 @@ extern "C" int svs_unet_forward_layers(const svs_unet_plan* plan, const svs_patc
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int li = first_layer; li <= last_layer; ++li) {
     int rc;
-    if (li == 0 && plan->c1_enabled && c1t_applicable(in, in_frames)) rc = c1t_launch(plan, ws, in, batch, st);
+    if (li == 0 && plan->c1z_enabled && c1t_applicable(in, in_frames)) rc = c1z_launch(plan, ws, in, batch, st);
+    else if (li == 0 && plan->c1_enabled && c1t_applicable(in, in_frames)) rc = c1t_launch(plan, ws, in, batch, st);
     else if (li == 11 && plan->d6_enabled) rc = d6_launch(plan, ws, in, out, in_frames, batch, flags, st);
     else if (plan->tc[li].enabled)
       rc = plan->zc[li].enabled ? zc_launch_layer(plan, li, ws, batch, st) : tc_launch_layer(plan, li, ws, batch, st);

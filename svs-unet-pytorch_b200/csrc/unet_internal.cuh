@@ -127,6 +127,9 @@ struct svs_unet_plan {
   void* c1_weights = nullptr;
   CUtensorMap c1_tmap_w;
   // deconv6 as a taps-as-N GEMM + col2im gather (deconv6_tc.cu)
+  bool c1z_enabled = false;          // conv1 with the image as the A operand (conv1_zc.cu); dense inputs
+  float* c1z_weights = nullptr;
+  CUtensorMap c1z_tmap_w;
   bool d6_enabled = false;
   void* d6_weights = nullptr;
   CUtensorMap d6_tmap_w;
