@@ -311,6 +311,9 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ix = r & 7, iy = r >> 3;
     int t = 0;
     OutT* const out_base = reinterpret_cast<OutT*>(p.out);
+    const float slope = p.act == ACT_LEAKY ? 0.2f : 0.0f;
+    const int cp_log2 = 31 - __clz(p.cout_phase), cp_mask = p.cout_phase - 1;   // channels per phase: a power of two
+    const uint32_t out_pitch = p.out_pitch, out_coff = p.out_coff;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, b = tile / (p.ntw * p.nth);
       const int gx = tw * kZcBw + ix, gy = th * kZcBh + iy;
@@ -320,6 +323,10 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccCols;
       constexpr int kStep = kBlockN >= 32 ? 32 : 16;
+      // The epilogue of tile t runs under the MMAs of tile t+1 with ONE warp per scheduler, so it is bound by
+      // dependent-issue latency: keep it short (branch-free activation, shifts, 32-bit offsets) or it, not the
+      // tensor pipe, sets the tile time of the small-N layers (deconv5: 36 MMAs = 1,728 cycles per tile).
+      const uint32_t pix0 = static_cast<uint32_t>((b * p.hout + gy * p.out_scale) * p.wout + gx * p.out_scale);
 #pragma unroll 2
       for (int c = 0; c < kBlockN; c += kStep) {
         uint32_t v[kStep];
@@ -328,22 +335,25 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tmem_ld_wait();
 #pragma unroll
         for (int h = 0; h < kStep; h += 16) {
-          int ch = c + h, py = 0, px = 0;
-          if (p.merged) {
-            const int ph = ch / p.cout_phase;
-            ch -= ph * p.cout_phase;
-            py = ph >> 1; px = ph & 1;
+          int ch = c + h;
+          uint32_t pix = pix0;
+          if (p.merged) {                                   // 16-column groups never straddle a phase
+            const int ph = ch >> cp_log2;
+            ch &= cp_mask;
+            pix += static_cast<uint32_t>((ph >> 1) * p.wout + (ph & 1));
           }
-          const int oy = gy * p.out_scale + py, ox = gx * p.out_scale + px;
-          OutT* dst = out_base + ((static_cast<size_t>(b) * p.hout + oy) * p.wout + ox) * p.out_pitch + p.out_coff + ch;
+          OutT* dst = out_base + (static_cast<size_t>(pix) * out_pitch + out_coff + ch);
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 bv = *reinterpret_cast<const float4*>(&sbias[ch + i]);
-            f[i] = zc_act(__uint_as_float(v[h + i]) + bv.x, p.act);
-            f[i + 1] = zc_act(__uint_as_float(v[h + i + 1]) + bv.y, p.act);
-            f[i + 2] = zc_act(__uint_as_float(v[h + i + 2]) + bv.z, p.act);
-            f[i + 3] = zc_act(__uint_as_float(v[h + i + 3]) + bv.w, p.act);
+            const float t0 = __uint_as_float(v[h + i]) + bv.x, t1 = __uint_as_float(v[h + i + 1]) + bv.y;
+            const float t2 = __uint_as_float(v[h + i + 2]) + bv.z, t3 = __uint_as_float(v[h + i + 3]) + bv.w;
+            // max(v, slope * v + 0): LeakyReLU (slope 0.2) or ReLU (slope 0) without a branch
+            f[i] = fmaxf(t0, fmaf(slope, t0, 0.0f));
+            f[i + 1] = fmaxf(t1, fmaf(slope, t1, 0.0f));
+            f[i + 2] = fmaxf(t2, fmaf(slope, t2, 0.0f));
+            f[i + 3] = fmaxf(t3, fmaf(slope, t3, 0.0f));
           }
           zc_store16(dst, f);
         }
