@@ -1,5 +1,6 @@
 """GPU: every kernel variant stays parity-green — the TMA-im2col kernels that the zero-copy kernels replaced,
-the un-merged transposed convolutions, split-K on/off, the CUDA-core edge layers, and launches without PDL."""
+the un-merged transposed convolutions, split-K on/off / across a cluster / through HBM, 128x256 tiles at large
+batch, both tensor-core conv1 kernels, the CUDA-core edge layers, and launches without PDL."""
 import os
 import subprocess
 import sys
@@ -18,7 +19,7 @@ from svs_unet_pytorch_b200 import model as svs_model
 torch.manual_seed(0)
 net = svs_model.UNet().eval()
 g = torch.Generator().manual_seed(1)
-x = torch.rand(5, 1, 512, 128, generator=g)
+x = torch.rand(int(os.environ.get("SVS_TEST_BATCH", "5")), 1, 512, 128, generator=g)
 with torch.no_grad():
     ref = unet_oracle.unet_forward(net.state_dict(), x)
 net = net.cuda()
@@ -39,6 +40,11 @@ VARIANTS = {
     "split_k_4": {"SVS_TC_SPLITK": "4"},
     "cuda_core_edges": {"SVS_TC_DISABLE_MASK": str((1 << 0) | (1 << 1) | (1 << 10) | (1 << 11))},
     "no_pdl": {"SVS_NO_PDL": "1"},
+    "split_k_through_hbm": {"SVS_TC_CLUSTER": "0"},                     # partial buffer + reduction kernel
+    "split_k_2_cluster": {"SVS_TC_SPLITK": "2"},
+    "conv1_im2col": {"SVS_C1Z_DISABLE": "1"},                           # conv1_tc_kernel instead of conv1_zc_kernel
+    "wide_tiles_large_batch": {"SVS_TEST_BATCH": "160"},                # conv5 / conv6 / deconv1 on 128 x 256 tiles
+    "narrow_tiles_large_batch": {"SVS_TEST_BATCH": "160", "SVS_TC_NO_WIDE": "1"},
 }
 
 
