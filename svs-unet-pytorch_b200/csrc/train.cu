@@ -224,6 +224,83 @@ wgrad_kernel(WgradArgs a, float* __restrict__ partial /*[splits][25][cin][cout]*
     }
 }
 
+// Layers with cin * cout <= 512 (conv1 1x16, conv2 16x32, deconv6 32x1): a 32 x 32 channel tile would be mostly
+// padding and the reduction runs over up to a million pixels.  64 pixels are staged per step with shift-decoded
+// coordinates (every grid dimension of this net is a power of two).  Thread = (pair, slice): `pairs_pad` (ci, co)
+// pairs (two per thread when there are 512) x 256 / pairs_pad pixel slices of the staged chunk; the slices are summed
+// in fixed order at the end, so the result is deterministic.
+__global__ void __launch_bounds__(256)
+wgrad_small_kernel(WgradArgs a, int gw_log2, int gh_log2, int sc_log2, int lc_log2, int pairs_log2,
+                   float* __restrict__ partial /*[splits][25][cin][cout]*/) {
+  __shared__ float ss[64 * 32], sl[64 * 32];
+  const int tap = blockIdx.x;
+  const int kh = tap / 5, kw = tap % 5;
+  const size_t npix = static_cast<size_t>(a.batch) << (gw_log2 + gh_log2);
+  const size_t per = (npix + gridDim.y - 1) / gridDim.y;
+  const size_t p_begin = blockIdx.y * per, p_end = min(npix, p_begin + per);
+  const int n_pairs = a.cin * a.cout;
+  const int pairs_pad = 1 << pairs_log2;                 // >= n_pairs, <= 512
+  const int per_thread = pairs_pad > 256 ? 2 : 1;
+  const int lanes_log2 = pairs_pad > 256 ? 8 : pairs_log2;
+  const int slices = 256 >> lanes_log2;                  // pixel slices of a chunk
+  const int lane_pair = threadIdx.x & ((1 << lanes_log2) - 1), slice = threadIdx.x >> lanes_log2;
+  // pair -> (S channel, L channel): conv S = dY (co), L = X (ci); deconv S = X (ci), L = dY (co)
+  int cs[2] = {0, 0}, cl[2] = {0, 0};
+  bool on[2] = {false, false};
+  for (int k = 0; k < per_thread; ++k) {
+    const int pr = lane_pair + 256 * k;
+    on[k] = pr < n_pairs;
+    const int ci = on[k] ? pr / a.cout : 0, co = on[k] ? pr % a.cout : 0;
+    cs[k] = a.s_is_cout ? co : ci;
+    cl[k] = a.s_is_cout ? ci : co;
+  }
+  float acc[2] = {0.f, 0.f};
+  const int lh = 2 << gh_log2, lw = 2 << gw_log2;
+  const int gw_mask = (1 << gw_log2) - 1, gh_mask = (1 << gh_log2) - 1;
+  for (size_t p0 = p_begin; p0 < p_end; p0 += 64) {
+    for (int e = threadIdx.x; e < (64 << sc_log2); e += 256) {
+      const int r = e >> sc_log2, c = e & (a.s_c - 1);
+      const size_t p = p0 + r;
+      ss[e] = p < p_end ? a.S[p * a.s_pitch + a.s_coff + c] : 0.f;
+    }
+    for (int e = threadIdx.x; e < (64 << lc_log2); e += 256) {
+      const int r = e >> lc_log2, c = e & (a.l_c - 1);
+      const size_t p = p0 + r;
+      float v = 0.f;
+      if (p < p_end) {
+        const int gx = static_cast<int>(p) & gw_mask, gy = static_cast<int>(p >> gw_log2) & gh_mask;
+        const int b = static_cast<int>(p >> (gw_log2 + gh_log2));
+        const int ly = 2 * gy + kh - 2, lx = 2 * gx + kw - 2;
+        if (ly >= 0 && ly < lh && lx >= 0 && lx < lw)
+          v = a.L[((static_cast<size_t>(b) * lh + ly) * lw + lx) * a.l_pitch + a.l_coff + c];
+      }
+      sl[e] = v;
+    }
+    __syncthreads();
+    if (on[0]) {
+#pragma unroll 4
+      for (int r = slice; r < 64; r += slices) {     // ascending pixel order within a slice
+        acc[0] = fmaf(ss[(r << sc_log2) + cs[0]], sl[(r << lc_log2) + cl[0]], acc[0]);
+        if (per_thread == 2) acc[1] = fmaf(ss[(r << sc_log2) + cs[1]], sl[(r << lc_log2) + cl[1]], acc[1]);
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = partial + (static_cast<size_t>(blockIdx.y) * 25 + tap) * n_pairs;
+  if (slices == 1) {
+    if (on[0]) dst[lane_pair] = acc[0];                    // pair index = ci * cout + co
+    if (per_thread == 2 && on[1]) dst[lane_pair + 256] = acc[1];
+  } else {
+    ss[threadIdx.x] = acc[0];                              // [slice][pair]
+    __syncthreads();
+    if (slice == 0 && on[0]) {
+      float t = 0.f;
+      for (int k = 0; k < slices; ++k) t += ss[(k << lanes_log2) + lane_pair];   // fixed order
+      dst[lane_pair] = t;
+    }
+  }
+}
+
 // sum the split partials (fixed order) and scatter to the torch layout
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
                                       int transposed, float* __restrict__ grad_w) {
@@ -352,10 +429,27 @@ struct TrainWs {
   size_t total;
 };
 
+static int ilog2_exact(int v) {
+  for (int k = 0; k < 31; ++k) if ((1 << k) == v) return k;
+  return -1;
+}
+// cin * cout <= 512 and power-of-two extents: wgrad_small_kernel
+static bool wgrad_is_small(int li) {
+  const LayerGeom& g = kLayers[li];
+  const int gh = g.transposed ? g.hin : g.hout, gw = g.transposed ? g.win : g.wout;
+  return g.cin * g.cout <= 512 && g.cin <= 32 && g.cout <= 32 && ilog2_exact(g.cin) >= 0 && ilog2_exact(g.cout) >= 0 &&
+         ilog2_exact(gh) >= 0 && ilog2_exact(gw) >= 0;
+}
+
 static int wgrad_splits(int li, int batch) {
   const LayerGeom& g = kLayers[li];
   const int gh = g.transposed ? g.hin : g.hout, gw = g.transposed ? g.win : g.wout;
   const size_t npix = static_cast<size_t>(batch) * gh * gw;
+  if (wgrad_is_small(li)) {                                      // 25 taps x splits CTAs of 256 threads
+    size_t s = 48;
+    const size_t max_small = (npix + 1023) / 1024;               // at least 1024 pixels per split
+    return static_cast<int>(s > max_small ? (max_small ? max_small : 1) : s);
+  }
   const int tiles = 25 * ((g.cin + 31) / 32) * ((g.cout + 31) / 32);
   int s = (148 * 16 + tiles - 1) / tiles;                        // ~16 CTAs of 64 threads per SM
   const size_t max_s = (npix + 255) / 256;                       // at least 256 pixels per split
@@ -487,9 +581,15 @@ static int run_wgrad(const TrainWs& w, const svs_train_layer& L, int li, int bat
     a.gh = g.hin; a.gw = g.win; a.s_is_cout = 0;
   }
   const int splits = wgrad_splits(li, batch);
-  dim3 grid(25, ((g.cin + 31) / 32) * ((g.cout + 31) / 32), splits);
-  wgrad_kernel<<<grid, 64, 0, st>>>(a, w.wgrad_partial);
-  SVS_CHECK_LAUNCH("wgrad_kernel");
+  if (wgrad_is_small(li)) {
+    wgrad_small_kernel<<<dim3(25, splits), 256, 0, st>>>(a, ilog2_exact(a.gw), ilog2_exact(a.gh), ilog2_exact(a.s_c),
+                                                        ilog2_exact(a.l_c), ilog2_exact(g.cin * g.cout), w.wgrad_partial);
+    SVS_CHECK_LAUNCH("wgrad_small_kernel");
+  } else {
+    dim3 grid(25, ((g.cin + 31) / 32) * ((g.cout + 31) / 32), splits);
+    wgrad_kernel<<<grid, 64, 0, st>>>(a, w.wgrad_partial);
+    SVS_CHECK_LAUNCH("wgrad_kernel");
+  }
   wgrad_finalize_kernel<<<grid_for(25 * g.cin * g.cout), 256, 0, st>>>(w.wgrad_partial, splits, g.cin, g.cout,
                                                                       g.transposed ? 1 : 0, L.grad_weight);
   SVS_CHECK_LAUNCH("wgrad_finalize_kernel");
