@@ -213,25 +213,32 @@ conv1_kernel(const float* __restrict__ in, const int64_t* __restrict__ patch_off
 
 // ---------------------------------------------------------------------------------------------
 // Generic direct 5x5 stride-2 convolution / transposed convolution over NHWC buffers.
-// One thread = one output pixel x 4 output channels; fp32 accumulate.
-template <typename T, bool kTransposed>
+// One thread = one output position x 4 output channels x kNB batch samples (b, b + B/kNB, ...); fp32 accumulate.
+// The samples share the tap validity and the weights, so each weight float4 is loaded once per kNB x 4 FMAs: the
+// kernel is bound by those loads, not by the FMAs.  Per output the accumulation order does not depend on kNB.
+template <typename T, bool kTransposed, int kNB>
 __global__ void __launch_bounds__(256)
 conv_direct_kernel(const T* __restrict__ in, int in_pitch, int in_coff, int hin, int win, int cin,
                    const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
                    int out_pitch, int out_coff, int hout, int wout, int cout, int act, int batch,
                    int accumulate) {
   const int cg_n = cout >> 2;
-  const size_t total = static_cast<size_t>(batch) * hout * wout * cg_n;
+  const int bgroups = batch / kNB;
+  const size_t total = static_cast<size_t>(bgroups) * hout * wout * cg_n;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cg = static_cast<int>(idx % cg_n);
   size_t pix = idx / cg_n;
   const int ow = static_cast<int>(pix % wout); pix /= wout;
   const int oh = static_cast<int>(pix % hout);
-  const int b = static_cast<int>(pix / hout);
+  const int b0 = static_cast<int>(pix / hout);
   const int co = cg * 4;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (bias) { acc[0] = bias[co]; acc[1] = bias[co + 1]; acc[2] = bias[co + 2]; acc[3] = bias[co + 3]; }
+  const size_t in_bstride = static_cast<size_t>(bgroups) * hin * win * in_pitch;
+  float acc[kNB][4];
+#pragma unroll
+  for (int n = 0; n < kNB; ++n)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[n][u] = bias ? bias[co + u] : 0.f;
   for (int kh = 0; kh < 5; ++kh) {
     int ih;
     if (kTransposed) {                     // oh = 2 ih - 2 + kh
@@ -252,30 +259,54 @@ conv_direct_kernel(const T* __restrict__ in, int in_pitch, int in_coff, int hin,
         iw = 2 * ow + kw - 2;
       }
       if (iw < 0 || iw >= win) continue;
-      const T* __restrict__ px = in + ((static_cast<size_t>(b) * hin + ih) * win + iw) * in_pitch + in_coff;
+      const T* __restrict__ px = in + ((static_cast<size_t>(b0) * hin + ih) * win + iw) * in_pitch + in_coff;
       const float* __restrict__ wt = w + static_cast<size_t>(kh * 5 + kw) * cin * cout + co;
       for (int ci = 0; ci < cin; ci += 8) {
-        float x[8];
-        load8(px + ci, x);
+        float x[kNB][8];
+#pragma unroll
+        for (int n = 0; n < kNB; ++n) load8(px + n * in_bstride + ci, x[n]);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const float4 wv = __ldg(reinterpret_cast<const float4*>(wt + static_cast<size_t>(ci + u) * cout));
-          acc[0] = fmaf(x[u], wv.x, acc[0]);
-          acc[1] = fmaf(x[u], wv.y, acc[1]);
-          acc[2] = fmaf(x[u], wv.z, acc[2]);
-          acc[3] = fmaf(x[u], wv.w, acc[3]);
+#pragma unroll
+          for (int n = 0; n < kNB; ++n) {
+            acc[n][0] = fmaf(x[n][u], wv.x, acc[n][0]);
+            acc[n][1] = fmaf(x[n][u], wv.y, acc[n][1]);
+            acc[n][2] = fmaf(x[n][u], wv.z, acc[n][2]);
+            acc[n][3] = fmaf(x[n][u], wv.w, acc[n][3]);
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) acc[u] = apply_act(acc[u], act);
-  T* dst = out + ((static_cast<size_t>(b) * hout + oh) * wout + ow) * out_pitch + out_coff + co;
-  if (accumulate) {
+  for (int n = 0; n < kNB; ++n) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] += to_float(dst[u]);
+    for (int u = 0; u < 4; ++u) acc[n][u] = apply_act(acc[n][u], act);
+    T* dst = out + ((static_cast<size_t>(b0 + n * bgroups) * hout + oh) * wout + ow) * out_pitch + out_coff + co;
+    if (accumulate) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[n][u] += to_float(dst[u]);
+    }
+    store4(dst, acc[n]);
   }
-  store4(dst, acc);
+}
+
+template <typename T, bool kTransposed>
+static void launch_conv_direct_any(const T* in, int in_pitch, int in_coff, int hin, int win, int cin, const float* w,
+                                   const float* bias, T* out, int out_pitch, int out_coff, int hout, int wout,
+                                   int cout, int act, int batch, int accumulate, cudaStream_t st) {
+  const int nb = batch % 4 == 0 ? 4 : (batch % 2 == 0 ? 2 : 1);
+  const size_t total = static_cast<size_t>(batch / nb) * hout * wout * (cout / 4);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+#define SVS_CD(NB)                                                                                                   \
+  conv_direct_kernel<T, kTransposed, NB><<<blocks, 256, 0, st>>>(in, in_pitch, in_coff, hin, win, cin, w, bias, out, \
+                                                                 out_pitch, out_coff, hout, wout, cout, act, batch,   \
+                                                                 accumulate)
+  if (nb == 4) SVS_CD(4);
+  else if (nb == 2) SVS_CD(2);
+  else SVS_CD(1);
+#undef SVS_CD
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -368,21 +399,16 @@ static int launch_layer_direct_t(const svs_unet_plan* plan, int li, const Worksp
     SVS_CHECK_LAUNCH("deconv6_kernel");
     return SVS_OK;
   }
-  const size_t total = static_cast<size_t>(batch) * g.hout * g.wout * (g.cout / 4);
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   const T* src = reinterpret_cast<const T*>(ws.buf[g.in_buf]);
   T* dst = reinterpret_cast<T*>(ws.buf[g.out_buf]);
-  if (g.transposed) {
-    conv_direct_kernel<T, true><<<blocks, 256, 0, st>>>(src, kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win,
-                                                       g.cin, plan->w_fold[li], plan->b_fold[li], dst,
-                                                       kBufGeom[g.out_buf].c, g.out_coff, g.hout, g.wout,
-                                                       g.cout, g.act, batch, 0);
-  } else {
-    conv_direct_kernel<T, false><<<blocks, 256, 0, st>>>(src, kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win,
-                                                        g.cin, plan->w_fold[li], plan->b_fold[li], dst,
-                                                        kBufGeom[g.out_buf].c, g.out_coff, g.hout, g.wout,
-                                                        g.cout, g.act, batch, 0);
-  }
+  if (g.transposed)
+    launch_conv_direct_any<T, true>(src, kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win, g.cin, plan->w_fold[li],
+                                    plan->b_fold[li], dst, kBufGeom[g.out_buf].c, g.out_coff, g.hout, g.wout, g.cout,
+                                    g.act, batch, 0, st);
+  else
+    launch_conv_direct_any<T, false>(src, kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win, g.cin, plan->w_fold[li],
+                                     plan->b_fold[li], dst, kBufGeom[g.out_buf].c, g.out_coff, g.hout, g.wout, g.cout,
+                                     g.act, batch, 0, st);
   SVS_CHECK_LAUNCH("conv_direct_kernel");
   return SVS_OK;
 }
@@ -391,16 +417,12 @@ static int launch_layer_direct_t(const svs_unet_plan* plan, int li, const Worksp
 int launch_conv_direct_f32(const float* in, int in_pitch, int in_coff, int hin, int win, int cin, const float* w,
                            const float* bias, float* out, int out_pitch, int out_coff, int hout, int wout,
                            int cout, int act, bool transposed, int batch, bool accumulate, cudaStream_t st) {
-  const size_t total = static_cast<size_t>(batch) * hout * wout * (cout / 4);
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   if (transposed)
-    conv_direct_kernel<float, true><<<blocks, 256, 0, st>>>(in, in_pitch, in_coff, hin, win, cin, w, bias, out,
-                                                           out_pitch, out_coff, hout, wout, cout, act, batch,
-                                                           accumulate ? 1 : 0);
+    launch_conv_direct_any<float, true>(in, in_pitch, in_coff, hin, win, cin, w, bias, out, out_pitch, out_coff, hout,
+                                        wout, cout, act, batch, accumulate ? 1 : 0, st);
   else
-    conv_direct_kernel<float, false><<<blocks, 256, 0, st>>>(in, in_pitch, in_coff, hin, win, cin, w, bias, out,
-                                                            out_pitch, out_coff, hout, wout, cout, act, batch,
-                                                            accumulate ? 1 : 0);
+    launch_conv_direct_any<float, false>(in, in_pitch, in_coff, hin, win, cin, w, bias, out, out_pitch, out_coff, hout,
+                                         wout, cout, act, batch, accumulate ? 1 : 0, st);
   SVS_CHECK_LAUNCH("conv_direct_kernel");
   return SVS_OK;
 }

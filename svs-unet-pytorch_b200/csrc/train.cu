@@ -171,7 +171,7 @@ struct WgradArgs {
 };
 
 __global__ void __launch_bounds__(64)
-wgrad_kernel(WgradArgs a, float* __restrict__ partial /*[splits][25][cin][cout]*/) {
+wgrad_kernel(WgradArgs a, int gw_log2, int gh_log2, float* __restrict__ partial /*[splits][25][cin][cout]*/) {
   __shared__ __align__(16) float ss[16][32], sl[16][32];
   const int tap = blockIdx.x;
   const int kh = tap / 5, kw = tap % 5;
@@ -191,9 +191,10 @@ wgrad_kernel(WgradArgs a, float* __restrict__ partial /*[splits][25][cin][cout]*
       const size_t p = p0 + r;
       float vs = 0.f, vl = 0.f;
       if (p < p_end) {
-        const int gx = static_cast<int>(p % a.gw);
-        const int gy = static_cast<int>((p / a.gw) % a.gh);
-        const int b = static_cast<int>(p / (static_cast<size_t>(a.gw) * a.gh));
+        // every grid extent of this net is a power of two: shifts, not 64-bit divisions
+        const int gx = static_cast<int>(p) & (a.gw - 1);
+        const int gy = static_cast<int>(p >> gw_log2) & (a.gh - 1);
+        const int b = static_cast<int>(p >> (gw_log2 + gh_log2));
         if (s0 + c < a.s_c) vs = a.S[p * a.s_pitch + a.s_coff + s0 + c];
         const int ly = 2 * gy + kh - 2, lx = 2 * gx + kw - 2;
         if (ly >= 0 && ly < lh && lx >= 0 && lx < lw && l0 + c < a.l_c)
@@ -587,7 +588,8 @@ static int run_wgrad(const TrainWs& w, const svs_train_layer& L, int li, int bat
     SVS_CHECK_LAUNCH("wgrad_small_kernel");
   } else {
     dim3 grid(25, ((g.cin + 31) / 32) * ((g.cout + 31) / 32), splits);
-    wgrad_kernel<<<grid, 64, 0, st>>>(a, w.wgrad_partial);
+    if (ilog2_exact(a.gw) < 0 || ilog2_exact(a.gh) < 0) return fail(SVS_ERR_INVALID_ARG, "run_wgrad: grid extents must be powers of two");
+    wgrad_kernel<<<grid, 64, 0, st>>>(a, ilog2_exact(a.gw), ilog2_exact(a.gh), w.wgrad_partial);
     SVS_CHECK_LAUNCH("wgrad_kernel");
   }
   wgrad_finalize_kernel<<<grid_for(25 * g.cin * g.cout), 256, 0, st>>>(w.wgrad_partial, splits, g.cin, g.cout,
