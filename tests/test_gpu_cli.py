@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import stft_oracle as so, unet_oracle  # noqa: E402
-from svs_unet_pytorch_b200 import audio_io, data, inference, model as svs_model, synth, train  # noqa: E402
+from svs_unet_pytorch_b200 import audio_io, data, inference, model as svs_model, separate, synth, train  # noqa: E402
 
 
 def _make_songs(root, n=2, seconds=13.0):
@@ -62,6 +62,42 @@ def test_to_spec_inference_to_wave(tmp_path):
         ry = so.to_wave(rpred, rphase)
         assert sr == 8192 and y.shape == ry.shape
         assert abs(synth.sdr_db(voc, y) - synth.sdr_db(voc, ry)) <= 0.05
+
+
+def test_fused_wav_to_wav_matches_the_three_stage_flow(tmp_path):
+    # one process, spectrograms stay in HBM; --emit_npy leaves the same files behind
+    src, spec_dir, pred_dir, wav_dir, out_dir, npy_dir = (str(tmp_path / n) for n in
+                                                          ("songs", "spec", "pred", "wav", "fused", "fused_npy"))
+    os.makedirs(src)
+    stems = _make_songs(src, n=3, seconds=11.0)
+    torch.manual_seed(0)
+    net = svs_model.UNet()
+    ckpt = str(tmp_path / "svs_test.pth")
+    torch.save({"epoch": 1, "model_state_dict": net.state_dict(), "optim": net.optim.state_dict(), "scheduler": None}, ckpt)
+    os.environ["SVS_B200_PRECISION"] = "tf32"
+    try:
+        data.main(["--src", src, "--tar", spec_dir, "--direction", "to_spec"])
+        inference.main(["--model_path", ckpt, "--mixture_folder", os.path.join(spec_dir, "mixture"), "--tar", pred_dir])
+        data.main(["--src", pred_dir, "--phase", spec_dir, "--tar", wav_dir, "--direction", "to_wave"])
+        separate.main(["--model_path", ckpt, "--src", src, "--tar", out_dir, "--emit_npy", npy_dir, "--songs_per_batch", "2"])
+    finally:
+        del os.environ["SVS_B200_PRECISION"]
+    sd = net.state_dict()
+    for i, (mix, voc) in enumerate(stems):
+        base = f"{i:04d}_song{i}"
+        y3, sr3 = audio_io.read_wav(os.path.join(wav_dir, base + ".wav"))
+        y1, sr1 = audio_io.read_wav(os.path.join(out_dir, base + ".wav"))
+        assert sr1 == sr3 == 8192 and y1.shape == y3.shape
+        assert np.abs(y1 - y3).max() <= 2e-3                           # both PCM_16; conv1 path may differ (dense vs view)
+        rspec, rphase, _ = so.to_spec(mix)
+        ry = so.to_wave(unet_oracle.separate_spectrogram(sd, rspec, vocal_solo=True), rphase)
+        assert abs(synth.sdr_db(voc, y1) - synth.sdr_db(voc, ry)) <= 0.05
+        for sub, name in (("mixture", base + "_spec.npy"), ("mixture", base + "_phase.npy")):
+            a, b = np.load(os.path.join(npy_dir, sub, name)), np.load(os.path.join(spec_dir, sub, name))
+            assert a.dtype == b.dtype and a.shape == b.shape and a.flags["F_CONTIGUOUS"] == b.flags["F_CONTIGUOUS"]
+            assert np.array_equal(a, b)
+        p1, p3 = np.load(os.path.join(npy_dir, base + "_spec.npy")), np.load(os.path.join(pred_dir, base + "_spec.npy"))
+        assert p1.shape == p3.shape and p1.dtype == p3.dtype and np.abs(p1 - p3).max() <= 1e-3
 
 
 def test_train_cli_one_epoch(tmp_path, monkeypatch):
