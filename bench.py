@@ -265,6 +265,22 @@ def run_ours(args):
     p1.record()
     barrier()
     ms_pipe = p0.elapsed_time(p1) / p_reps
+    # the same corpus from pinned host audio to pinned host waveforms: chunks of songs on
+    # alternating streams so the PCIe copies of one chunk overlap the kernels of the others
+    host_audio = audio.cpu().pin_memory()
+    host_wave = torch.empty(sbatch.total_wave, dtype=torch.float32).pin_memory()
+    streamer = pipeline.SongStreamer(net)
+    song_lengths = [n_samp] * len(mine)
+    for _ in range(2):
+        streamer.run(host_audio, song_lengths, host_wave)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(p_reps):
+        streamer.run(host_audio, song_lengths, host_wave)
+    h1.record()
+    barrier()
+    ms_pipe_host = h0.elapsed_time(h1) / p_reps
 
     # ---- the tcgen05 conv family alone (layers conv2..deconv5) as one CUDA graph: its device time per step ----
     g_tc = torch.cuda.CUDAGraph()
@@ -304,10 +320,10 @@ def run_ours(args):
         ms_tf32 = q0.elapsed_time(q1) / n32
         del plan32, net32
 
-    times = torch.tensor([ms_dev, ms_e2e, ms_pipe], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_dev, ms_e2e, ms_pipe, ms_pipe_host], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e, ms_pipe = float(times[0]), float(times[1]), float(times[2])
+    ms_dev, ms_e2e, ms_pipe, ms_pipe_host = (float(times[i]) for i in range(4))
 
     if rank == 0:
         peaks = measured_peaks()
@@ -353,7 +369,12 @@ def run_ours(args):
                                      "STFT -> /max -> UNet mask x mixture -> iSTFT -> 0.9 peak",
                          "audio_sec_per_sec": corpus * seconds / (ms_pipe * 1e-3), "ms_per_corpus": ms_pipe,
                          "patches_per_sec": corpus * 16 / (ms_pipe * 1e-3),
-                         "unet_batch": sep.max_batch, "patch_staging": "svs_patches_gather / svs_patches_scatter"},
+                         "unet_batch": sep.max_batch, "patch_staging": "svs_patches_gather / svs_patches_scatter",
+                         "host_to_host": {"audio_sec_per_sec": corpus * seconds / (ms_pipe_host * 1e-3),
+                                          "ms_per_corpus": ms_pipe_host,
+                                          "h2d_bytes": len(mine) * n_samp * 4, "d2h_bytes": int(sbatch.total_wave) * 4,
+                                          "api": "pipeline.SongStreamer.run (pinned host audio -> pinned host "
+                                                 "waveforms, 10-song chunks on four streams; PCIe bound)"}},
             "tflops_exact_whole_net": value * GFLOP_EXACT_PER_PATCH / 1e3,
             "tf32": None if ms_tf32 is None else {"patches_per_sec_per_gpu": BATCH / (ms_tf32 * 1e-3), "ms_per_step": ms_tf32,
                                                   "note": "same workload on the kind::tf32 path, direct launches (no graph), rank 0"},

@@ -44,18 +44,22 @@ class Separator:
         self.model = model
         self.max_batch = int(max_batch)
         self.staged = bool(staged)      # False: the UNet reads / writes the spectrogram through strided patch views
-        self._table_key, self._table_val = None, None
+        self._tables: dict = {}
 
     def _table(self, batch: SongBatch, dev):
-        """Patch table of a song batch on the device; cached for the last batch geometry (a corpus of equal-length
-        songs re-uses it, and building it costs a host loop plus three small H2D copies while the GPU idles)."""
+        """Patch table of a song batch on the device; the last few batch geometries are cached (a corpus of
+        equal-length songs re-uses them, and building one costs a host loop plus three small synchronous H2D copies
+        while the GPU idles)."""
         key = (tuple(batch.frames), str(dev))
-        if key != self._table_key:
+        val = self._tables.get(key)
+        if val is None:
             offs, valid, song = patch_table(batch.frames, batch.frame_off_host)
-            self._table_val = (offs, torch.from_numpy(offs).to(dev), torch.from_numpy(valid).to(dev),
-                               torch.from_numpy(song).to(dev).long())
-            self._table_key = key
-        return self._table_val
+            val = (offs, torch.from_numpy(offs).to(dev), torch.from_numpy(valid).to(dev),
+                   torch.from_numpy(song).to(dev).long())
+            if len(self._tables) >= 8:
+                self._tables.pop(next(iter(self._tables)))
+            self._tables[key] = val
+        return val
 
     @torch.no_grad()
     def separate_batch(self, batch: SongBatch, vocal_solo: bool = True, peak_normalize: bool = True,
@@ -103,6 +107,48 @@ class Separator:
         host = wave.cpu().numpy()
         return [host[int(batch.wave_off_host[s]): int(batch.wave_off_host[s]) + batch.wave_lengths[s]]
                 for s in range(batch.n_songs)]
+
+
+class SongStreamer:
+    """Host-buffer entry point for whole songs (BASELINE configs[3] end to end): pinned host audio -> device ->
+    STFT -> UNet mask -> iSTFT -> pinned host waveforms.  Songs are processed in chunks on alternating streams;
+    inside a stream a chunk's H2D copy, kernels and D2H copy are ordered, across the streams the copies of one chunk
+    overlap the kernels and the opposite-direction copies of the others (one DMA engine per direction).  This is the data.py -> inference.py -> data.py
+    chain of the reference with the four .npy files per song replaced by HBM."""
+
+    def __init__(self, model, songs_per_chunk: int = 10, vocal_solo: bool = True, n_streams: int = 4):
+        self.sep = Separator(model)
+        self.songs_per_chunk = int(songs_per_chunk)
+        self.vocal_solo = vocal_solo
+        self.dev = next(model.parameters()).device
+        self.streams = [torch.cuda.Stream(self.dev) for _ in range(max(1, int(n_streams)))]
+
+    @torch.no_grad()
+    def run(self, host_audio: torch.Tensor, lengths, host_wave: torch.Tensor):
+        """host_audio: pinned float32 [sum(lengths)] (songs back to back); host_wave: pinned float32
+        [sum(768 * (len // 768))] receiving the separated songs back to back.  Returns per-song wave lengths."""
+        n = len(lengths)
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.streams:
+            s.wait_stream(cur)
+        in_off, out_off, wave_lengths = 0, 0, []
+        keep = []                                                     # device tensors stay referenced until the join
+        for ci, a in enumerate(range(0, n, self.songs_per_chunk)):
+            lens = [int(v) for v in lengths[a:a + self.songs_per_chunk]]
+            n_in = sum(lens)
+            st = self.streams[ci % len(self.streams)]
+            with torch.cuda.stream(st):
+                audio = host_audio[in_off:in_off + n_in].to(self.dev, non_blocking=True)
+                batch = SongBatch(audio, lens)
+                wave, _ = self.sep.separate_batch(batch, self.vocal_solo, True)
+                host_wave[out_off:out_off + batch.total_wave].copy_(wave, non_blocking=True)
+                keep.append((audio, wave))
+            wave_lengths += batch.wave_lengths
+            in_off += n_in
+            out_off += batch.total_wave
+        for s in self.streams:
+            cur.wait_stream(s)
+        return wave_lengths
 
 
 class PatchStreamer:

@@ -33,6 +33,8 @@ def _device(device=None) -> torch.device:
 class SongBatch:
     """A ragged batch of mono songs resident on the device (concatenated samples + offset tables)."""
 
+    _offset_cache: dict = {}
+
     def __init__(self, audio: torch.Tensor, lengths: list[int]):
         _lib.require_cuda(audio, "audio", torch.float32)
         self.audio = audio
@@ -41,13 +43,20 @@ class SongBatch:
         self.frames = [1 + n // HOP_SIZE for n in self.lengths]           # librosa: 1 + len // hop
         self.wave_lengths = [HOP_SIZE * (t - 1) for t in self.frames]     # istft: hop * (T - 1)
         dev = audio.device
-        so = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.int64)
-        fo = np.concatenate([[0], np.cumsum(self.frames)]).astype(np.int64)
-        wo = np.concatenate([[0], np.cumsum(self.wave_lengths)]).astype(np.int64)
+        # offset tables of the last few batch geometries stay on the device: building them costs three small
+        # synchronous H2D copies, which stall a pipelined caller (SongStreamer) on every chunk
+        key = (tuple(self.lengths), str(dev))
+        hit = SongBatch._offset_cache.get(key)
+        if hit is None:
+            so = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.int64)
+            fo = np.concatenate([[0], np.cumsum(self.frames)]).astype(np.int64)
+            wo = np.concatenate([[0], np.cumsum(self.wave_lengths)]).astype(np.int64)
+            hit = (so, fo, wo, torch.from_numpy(so).to(dev), torch.from_numpy(fo).to(dev), torch.from_numpy(wo).to(dev))
+            if len(SongBatch._offset_cache) >= 8:
+                SongBatch._offset_cache.pop(next(iter(SongBatch._offset_cache)))
+            SongBatch._offset_cache[key] = hit
+        so, fo, wo, self.sample_off, self.frame_off, self.wave_off = hit
         self.sample_off_host, self.frame_off_host, self.wave_off_host = so, fo, wo
-        self.sample_off = torch.from_numpy(so).to(dev)
-        self.frame_off = torch.from_numpy(fo).to(dev)
-        self.wave_off = torch.from_numpy(wo).to(dev)
         self.total_frames = int(fo[-1])
         self.total_wave = int(wo[-1])
         self.max_frames = max(self.frames)
