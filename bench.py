@@ -269,15 +269,15 @@ def run_ours(args):
     # alternating streams so the PCIe copies of one chunk overlap the kernels of the others
     host_audio = audio.cpu().pin_memory()
     host_wave = torch.empty(sbatch.total_wave, dtype=torch.float32).pin_memory()
-    streamer = pipeline.SongStreamer(net)
+    song_streamer = pipeline.SongStreamer(net)
     song_lengths = [n_samp] * len(mine)
     for _ in range(2):
-        streamer.run(host_audio, song_lengths, host_wave)
+        song_streamer.run(host_audio, song_lengths, host_wave)
     barrier()
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h0.record()
     for _ in range(p_reps):
-        streamer.run(host_audio, song_lengths, host_wave)
+        song_streamer.run(host_audio, song_lengths, host_wave)
     h1.record()
     barrier()
     ms_pipe_host = h0.elapsed_time(h1) / p_reps
