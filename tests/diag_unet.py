@@ -1,4 +1,5 @@
-"""GPU diagnostic: per-layer error of the CUDA UNet against the CPU oracle (not part of the product)."""
+"""GPU diagnostic (test infrastructure, lives under tests/ because it uses the oracle): per-layer error of the CUDA
+UNet against the CPU oracle.   python tests/diag_unet.py [batch] [fp32,bf16,tf32]"""
 import os
 import sys
 import time
