@@ -52,6 +52,23 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   float2 twp[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) twp[q] = __ldg(&tw1024[j + 64 * q]);
+  // synthesis window x 1/512 for the samples this thread produces (n = jj + 64 d -> samples 2n, 2n + 1), in registers
+  const int jj = (j >> 3) + 8 * (j & 7);
+  // Samples 256..767 of a frame are covered by that frame alone, so their envelope reciprocal 1 / w^2 is folded into
+  // the window factor here (one rounding apart from (x w) / w^2); samples < 256 and >= 768 overlap a neighbour and
+  // keep the plain window until the two frames have been added.
+  float2 wsc[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    const int s0 = 2 * (jj + 64 * d);
+    const float2 wv = __ldg(reinterpret_cast<const float2*>(hann) + jj + 64 * d);
+    const bool single = s0 >= SVS_N_FFT - SVS_HOP && s0 < SVS_HOP;          // s0 even: s0 + 1 is in the same region
+    const float e0 = single ? __ldg(&env_single[s0]) : 1.0f, e1 = single ? __ldg(&env_single[s0 + 1]) : 1.0f;
+    wsc[d] = make_float2(wv.x * (1.0f / 512.0f) * e0, -wv.y * (1.0f / 512.0f) * e1);
+  }
+  float envb[4];                                   // 1 / (w^2[r + 768] + w^2[r]) for this thread's r = j + 64 c < 256
+#pragma unroll
+  for (int c = 0; c < 4; ++c) envb[c] = __ldg(&env_both[j + 64 * c]);
 
   const int64_t w0 = wave_off[song];
   const int out_len = SVS_HOP * (n_frames - 1);                 // librosa: hop * (T - 1) after trimming
@@ -101,13 +118,10 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
     group_bar(bar);                                          // pass A rewrites buffer X
     fft512_group(v, tw, scratch, j, bar);
     // v[d] = FFT(conj Z)[n], n = jj + 64 d ;  z[n] = conj(v)/512 ;  x[2n] = Re, x[2n+1] = Im
-    const int jj = (j >> 3) + 8 * (j & 7);
-    const float sc = 1.0f / 512.0f;
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
       const int n = jj + 64 * d;
-      const float2 wv = __ldg(reinterpret_cast<const float2*>(hann) + n);
-      *reinterpret_cast<float2*>(&fr[2 * n]) = make_float2(v[d].x * sc * wv.x, -v[d].y * sc * wv.y);
+      *reinterpret_cast<float2*>(&fr[2 * n]) = make_float2(v[d].x * wsc[d].x, v[d].y * wsc[d].y);
     }
     group_bar(bar);
     // ---- emit hop segment t (gather form: frame t-1's tail + frame t), then keep frame t's tail ----
@@ -119,9 +133,9 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
       if (emit) {
         const int p = t * SVS_HOP + r - SVS_N_FFT / 2;        // output sample index
         if (p >= 0 && p < out_len) {
-          float val;
-          if (r < SVS_N_FFT - SVS_HOP && t > 0) val = (tail[r] + cur) * __ldg(&env_both[r]);   // t-1 added first
-          else val = cur * __ldg(&env_single[r]);
+          // r < 256: frame t-1's tail is added first, then the two-frame envelope (t = 0 never gets here: p < 0);
+          // r >= 256: already divided by its envelope when it was windowed
+          const float val = c < 4 ? (tail[r] + cur) * envb[c & 3] : cur;
           wave[w0 + p] = val;
           peak = fmaxf(peak, fabsf(val));
         }
