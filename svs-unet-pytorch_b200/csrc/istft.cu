@@ -19,13 +19,13 @@ namespace svs {
 constexpr int kIstftThreads = 256;
 constexpr int kIstftRun = 16;                    // consecutive hop segments owned by one 64-thread group
 constexpr int kIstftGroupFloats = kFftGroupFloats + 1024 + 256;   // FFT scratch + windowed frame + previous tail
-constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats + sizeof(float2) * kFftTwiddleFloat2;
+constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats;
 
 // One 64-thread group walks kIstftRun + 1 consecutive frames of one song: frame t-1's last 256 windowed
 // samples (its "tail") stay in shared memory and are added to the first 256 samples of frame t when the
 // group emits hop segment t.  The first frame of a run is transformed only for its tail (1/16 redundant
 // transforms), so groups and CTAs never depend on each other and every output sample is written once.
-__global__ void __launch_bounds__(kIstftThreads)
+__global__ void __launch_bounds__(kIstftThreads, 2)
 istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase,
                  const int64_t* __restrict__ frame_off, const int64_t* __restrict__ wave_off,
                  float* __restrict__ wave, float* __restrict__ song_peak,
@@ -38,9 +38,8 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   const int group = threadIdx.x >> 6;
   const int j = threadIdx.x & 63;
   const int seg_begin = (blockIdx.x * 4 + group) * kIstftRun;   // first segment (= frame index) of this group
-  float2* tw_table = reinterpret_cast<float2*>(smem + 4 * kIstftGroupFloats);
-  const FftTwiddles tw = build_fft_twiddles(tw_table, tw1024, threadIdx.x, kIstftThreads, j);
-  __syncthreads();
+  FftTwiddlesReg tw;
+  load_fft_twiddles(tw, tw1024, j);
   if (seg_begin >= n_frames) return;                            // whole group leaves (barriers are per group)
   float* scratch = smem + group * kIstftGroupFloats;
   float* xre = scratch;
