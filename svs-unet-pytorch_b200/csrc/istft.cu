@@ -8,8 +8,8 @@
 //
 // With padded position P = p + 512:  frame t covers P in [768 t, 768 t + 1024).  Segment t =
 // [768 t, 768 t + 768) receives frame t (offset r = P - 768 t) and, for r < 256, frame t-1
-// (offset r + 768).  A 64-thread group owns 16 consecutive segments of one song and transforms 17
-// frames (the first one only for its tail), i.e. 1/16 redundant transforms and no dependency
+// (offset r + 768).  A 64-thread group owns 32 consecutive segments of one song and transforms 33
+// frames (the first one only for its tail), i.e. 1/32 redundant transforms and no dependency
 // between groups or CTAs.
 #include "svs_common.cuh"
 #include "fft512.cuh"
@@ -17,13 +17,13 @@
 namespace svs {
 
 constexpr int kIstftThreads = 256;
-constexpr int kIstftRun = 16;                    // consecutive hop segments owned by one 64-thread group
+constexpr int kIstftRun = 32;                    // consecutive hop segments owned by one 64-thread group
 constexpr int kIstftGroupFloats = kFftGroupFloats + 1024 + 256;   // FFT scratch + windowed frame + previous tail
 constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats;
 
 // One 64-thread group walks kIstftRun + 1 consecutive frames of one song: frame t-1's last 256 windowed
 // samples (its "tail") stay in shared memory and are added to the first 256 samples of frame t when the
-// group emits hop segment t.  The first frame of a run is transformed only for its tail (1/16 redundant
+// group emits hop segment t.  The first frame of a run is transformed only for its tail (1/32 redundant
 // transforms), so groups and CTAs never depend on each other and every output sample is written once.
 __global__ void __launch_bounds__(kIstftThreads, 2)
 istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase,
