@@ -18,7 +18,7 @@ namespace svs {
 
 constexpr int kIstftThreads = 256;
 constexpr int kIstftRun = 32;                    // consecutive hop segments owned by one 64-thread group
-constexpr int kIstftGroupFloats = kFftGroupFloats + 1024 + 256;   // FFT scratch + windowed frame + previous tail
+constexpr int kIstftGroupFloats = kFftGroupFloats + 2 * 1024;   // FFT scratch + two windowed frames (ping-pong)
 constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats;
 
 // One 64-thread group walks kIstftRun + 1 consecutive frames of one song: frame t-1's last 256 windowed
@@ -44,8 +44,10 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   float* scratch = smem + group * kIstftGroupFloats;
   float* xre = scratch;
   float* xim = scratch + kFftScratchFloats;
-  float* fr = scratch + kFftGroupFloats;                        // [1024] windowed frame
-  float* tail = fr + 1024;                                      // [256]  frame t-1, samples 768..1023
+  // windowed frames ping-pong between two buffers: frame t-1's samples 768..1023 (its "tail") are read in place when
+  // segment t is emitted -- no tail copy, and no barrier at the end of a frame (the buffer written next is the one
+  // that was read two barriers-full frames ago)
+  float* const fr_buf = scratch + kFftGroupFloats;              // [2][1024]
   const int bar = 1 + group;
 
   float2 twp[4];
@@ -76,8 +78,10 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   for (int slot = 0; slot <= kIstftRun; ++slot) {
     const int t = seg_begin - 1 + slot;
     if (t >= n_frames) break;
+    float* const fr = fr_buf + (slot & 1) * 1024;
+    const float* const tail = fr_buf + ((slot & 1) ^ 1) * 1024 + SVS_HOP;   // frame t-1, samples 768..1023
     if (t < 0) {                                                // no frame before the first: empty tail
-      for (int i = j; i < 256; i += 64) tail[i] = 0.0f;
+      for (int i = j; i < 256; i += 64) fr[SVS_HOP + i] = 0.0f;
       group_bar(bar);
       continue;
     }
@@ -140,9 +144,6 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tail[j + 64 * c] = fr[SVS_HOP + j + 64 * c];   // same thread read tail[r] above
-    group_bar(bar);                                          // fr / scratch are rewritten by the next frame
   }
   if (song_peak != nullptr) {
     peak = warp_max(peak);
