@@ -18,7 +18,8 @@ namespace svs {
 
 constexpr int kIstftThreads = 256;
 constexpr int kIstftRun = 32;                    // consecutive hop segments owned by one 64-thread group
-constexpr int kIstftGroupFloats = kFftGroupFloats + 2 * 1024;   // FFT scratch + two windowed frames (ping-pong)
+constexpr int kIstftFrFloats = 1024 + 128;                      // windowed frame, 4 floats of padding per 32 (z_addr)
+constexpr int kIstftGroupFloats = kFftGroupFloats + 2 * kIstftFrFloats;   // FFT scratch + two windowed frames (ping-pong)
 constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats;
 
 // One 64-thread group walks kIstftRun + 1 consecutive frames of one song: frame t-1's last 256 windowed
@@ -47,7 +48,10 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   // windowed frames ping-pong between two buffers: frame t-1's samples 768..1023 (its "tail") are read in place when
   // segment t is emitted -- no tail copy, and no barrier at the end of a frame (the buffer written next is the one
   // that was read two barriers-full frames ago)
-  float* const fr_buf = scratch + kFftGroupFloats;              // [2][1024]
+  // Sample s lives at z_addr(s) = s + 4 (s >> 5): the producer's 8-byte stores (sample pairs 2n, n = jj + 64 d, i.e.
+  // a stride of 16 floats across lanes) and the emitter's 4-byte loads of 32 consecutive samples are then both
+  // bank-conflict free; the dense layout cost a 4-way conflict on every store (a third of all wavefronts: ncu).
+  float* const fr_buf = scratch + kFftGroupFloats;              // [2][kIstftFrFloats]
   const int bar = 1 + group;
 
   float2 twp[4];
@@ -78,10 +82,10 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   for (int slot = 0; slot <= kIstftRun; ++slot) {
     const int t = seg_begin - 1 + slot;
     if (t >= n_frames) break;
-    float* const fr = fr_buf + (slot & 1) * 1024;
-    const float* const tail = fr_buf + ((slot & 1) ^ 1) * 1024 + SVS_HOP;   // frame t-1, samples 768..1023
+    float* const fr = fr_buf + (slot & 1) * kIstftFrFloats;
+    const float* const prev = fr_buf + ((slot & 1) ^ 1) * kIstftFrFloats;   // frame t-1: its samples 768..1023 are the tail
     if (t < 0) {                                                // no frame before the first: empty tail
-      for (int i = j; i < 256; i += 64) fr[SVS_HOP + i] = 0.0f;
+      for (int i = j; i < 256; i += 64) fr[z_addr(SVS_HOP + i)] = 0.0f;
       group_bar(bar);
       continue;
     }
@@ -124,7 +128,7 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
       const int n = jj + 64 * d;
-      *reinterpret_cast<float2*>(&fr[2 * n]) = make_float2(v[d].x * wsc[d].x, v[d].y * wsc[d].y);
+      *reinterpret_cast<float2*>(&fr[z_addr(2 * n)]) = make_float2(v[d].x * wsc[d].x, v[d].y * wsc[d].y);
     }
     group_bar(bar);
     // ---- emit hop segment t (gather form: frame t-1's tail + frame t), then keep frame t's tail ----
@@ -132,13 +136,13 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
 #pragma unroll
     for (int c = 0; c < SVS_HOP / 64; ++c) {
       const int r = j + 64 * c;
-      const float cur = fr[r];
+      const float cur = fr[z_addr(r)];
       if (emit) {
         const int p = t * SVS_HOP + r - SVS_N_FFT / 2;        // output sample index
         if (p >= 0 && p < out_len) {
           // r < 256: frame t-1's tail is added first, then the two-frame envelope (t = 0 never gets here: p < 0);
           // r >= 256: already divided by its envelope when it was windowed
-          const float val = c < 4 ? (tail[r] + cur) * envb[c & 3] : cur;
+          const float val = c < 4 ? (prev[z_addr(SVS_HOP + r)] + cur) * envb[c & 3] : cur;
           wave[w0 + p] = val;
           peak = fmaxf(peak, fabsf(val));
         }
