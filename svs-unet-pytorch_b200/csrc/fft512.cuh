@@ -98,14 +98,14 @@ __device__ __forceinline__ FftTwiddles build_fft_twiddles(float2* table, const f
 __device__ __forceinline__ int z_addr(int k) { return k + 4 * (k >> 5); }
 
 // Forward FFT of the 64-thread group.  in: v[n1] = z[j + 64 n1].  out: v[d] = Z[jj + 64 d] with
-// jj = (j >> 3) + 8 (j & 7).  `scratch` = this group's kFftGroupFloats floats.  On return the
-// caller may overwrite buffer X only after a further group_bar (see callers).
+// jj = (j >> 3) + 8 (j & 7).  `xbuf` / `ybuf` = this group's exchange buffers X and Y (2 * kFftScratchFloats floats
+// each).  On return every thread has finished with X; Y may be overwritten only after a further group_bar.
 template <typename TW>
-__device__ __forceinline__ void fft512_group(float2 (&v)[8], const TW& tw, float* scratch, int j, int bar) {
-  float* xre = scratch;
-  float* xim = scratch + kFftScratchFloats;
-  float* yre = scratch + 2 * kFftScratchFloats;
-  float* yim = scratch + 3 * kFftScratchFloats;
+__device__ __forceinline__ void fft512_group(float2 (&v)[8], const TW& tw, float* xbuf, float* ybuf, int j, int bar) {
+  float* xre = xbuf;
+  float* xim = xbuf + kFftScratchFloats;
+  float* yre = ybuf;
+  float* yim = ybuf + kFftScratchFloats;
   // pass A: radix-8 over n1, twiddle W_512^{j k1}
   dft8(v);
 #pragma unroll

@@ -19,14 +19,15 @@ namespace svs {
 constexpr int kIstftThreads = 256;
 constexpr int kIstftRun = 32;                    // consecutive hop segments owned by one 64-thread group
 constexpr int kIstftFrFloats = 1024 + 128;                      // windowed frame, 4 floats of padding per 32 (z_addr)
-constexpr int kIstftGroupFloats = kFftGroupFloats + 2 * kIstftFrFloats;   // FFT scratch + two windowed frames (ping-pong)
-constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats;
+constexpr int kIstftGroupFloats = 2 * kFftScratchFloats + 2 * kIstftFrFloats;   // exchange buffer X + two windowed frames
+                                                                // (ping-pong); the current one doubles as exchange buffer Y
+constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats + sizeof(float2) * kFftTwiddleFloat2;
 
 // One 64-thread group walks kIstftRun + 1 consecutive frames of one song: frame t-1's last 256 windowed
 // samples (its "tail") stay in shared memory and are added to the first 256 samples of frame t when the
 // group emits hop segment t.  The first frame of a run is transformed only for its tail (1/32 redundant
 // transforms), so groups and CTAs never depend on each other and every output sample is written once.
-__global__ void __launch_bounds__(kIstftThreads, 2)
+__global__ void __launch_bounds__(kIstftThreads, 3)
 istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase,
                  const int64_t* __restrict__ frame_off, const int64_t* __restrict__ wave_off,
                  float* __restrict__ wave, float* __restrict__ song_peak,
@@ -39,8 +40,9 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   const int group = threadIdx.x >> 6;
   const int j = threadIdx.x & 63;
   const int seg_begin = (blockIdx.x * 4 + group) * kIstftRun;   // first segment (= frame index) of this group
-  FftTwiddlesReg tw;
-  load_fft_twiddles(tw, tw1024, j);
+  float2* tw_table = reinterpret_cast<float2*>(smem + 4 * kIstftGroupFloats);
+  const FftTwiddles tw = build_fft_twiddles(tw_table, tw1024, threadIdx.x, kIstftThreads, j);
+  __syncthreads();
   if (seg_begin >= n_frames) return;                            // whole group leaves (barriers are per group)
   float* scratch = smem + group * kIstftGroupFloats;
   float* xre = scratch;
@@ -51,7 +53,7 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   // Sample s lives at z_addr(s) = s + 4 (s >> 5): the producer's 8-byte stores (sample pairs 2n, n = jj + 64 d, i.e.
   // a stride of 16 floats across lanes) and the emitter's 4-byte loads of 32 consecutive samples are then both
   // bank-conflict free; the dense layout cost a 4-way conflict on every store (a third of all wavefronts: ncu).
-  float* const fr_buf = scratch + kFftGroupFloats;              // [2][kIstftFrFloats]
+  float* const fr_buf = scratch + 2 * kFftScratchFloats;        // [2][kIstftFrFloats]
   const int bar = 1 + group;
 
   float2 twp[4];
@@ -123,7 +125,8 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
       v[n1] = make_float2(xre[a], xim[a]);
     }
     group_bar(bar);                                          // pass A rewrites buffer X
-    fft512_group(v, tw, scratch, j, bar);
+    fft512_group(v, tw, scratch, fr, j, bar);                // exchange buffer Y = this frame's (still empty) fr buffer
+    group_bar(bar);                                          // every thread has read Y before it becomes `fr`
     // v[d] = FFT(conj Z)[n], n = jj + 64 d ;  z[n] = conj(v)/512 ;  x[2n] = Re, x[2n+1] = Im
 #pragma unroll
     for (int d = 0; d < 8; ++d) {

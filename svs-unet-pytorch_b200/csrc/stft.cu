@@ -93,7 +93,7 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) v[n1] = make_float2(nxt[n1].x * win[n1].x, nxt[n1].y * win[n1].y);
     if (t + 4 < t_end) load_frame(t + 4, nxt);
-    fft512_group(v, tw, scratch, j, bar);
+    fft512_group(v, tw, scratch, scratch + 2 * kFftScratchFloats, j, bar);
     // ---- exchange 3: Z[k] in padded linear order ----
     const int jj = (j >> 3) + 8 * (j & 7);
 #pragma unroll
