@@ -34,7 +34,7 @@ __device__ __forceinline__ void mag_phase(float2 x, float& m, float2& ph) {
 }
 
 template <bool kComplexOut>
-__global__ void __launch_bounds__(kStftThreads, 2)
+__global__ void __launch_bounds__(kStftThreads, 3)
 stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict__ sample_off,
                       const int64_t* __restrict__ frame_off, float* __restrict__ mag,
                       float2* __restrict__ phase, float* __restrict__ song_max,
@@ -58,8 +58,9 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
 
   // per-thread constants in registers: window taps, FFT twiddles, split-step twiddles (the kernel's limiter
   // is shared-memory bandwidth, so tables in shared memory cost more than the occupancy they buy: measured)
-  FftTwiddlesReg tw;
-  load_fft_twiddles(tw, tw1024, j);
+  __shared__ float2 tw_table[kFftTwiddleFloat2];
+  const FftTwiddles tw = build_fft_twiddles(tw_table, tw1024, threadIdx.x, kStftThreads, j);
+  __syncthreads();
   float2 win[8];
 #pragma unroll
   for (int n1 = 0; n1 < 8; ++n1) win[n1] = __ldg(reinterpret_cast<const float2*>(hann) + j + 64 * n1);
