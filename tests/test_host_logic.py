@@ -30,6 +30,27 @@ def test_cli_flags_match_reference():
     assert (t.epoch, t.batch_size, t.val_interval, t.load_path) == (2, 2, 20, "result.pth")           # train.py:157-167
 
 
+def test_fused_cli_song_discovery_and_no_cpu_path(tmp_path):
+    # scripts/separate.py: same enumeration order as reference data.py:56 (sorted folder names), plain wav fallback,
+    # and -- like every product entry point -- it refuses to run without a GPU instead of falling back
+    from svs_unet_pytorch_b200 import _lib, audio_io, separate
+    y = np.zeros(8192, dtype=np.float32)
+    for name in ("b_song", "a_song", "no_mixture"):
+        os.makedirs(tmp_path / "songs" / name)
+    audio_io.write_wav_pcm16(str(tmp_path / "songs" / "b_song" / "mixture.wav"), y, 8192)
+    audio_io.write_wav_pcm16(str(tmp_path / "songs" / "a_song" / "mixture.wav"), y, 8192)
+    found = separate.find_songs(str(tmp_path / "songs"))
+    assert [n for n, _ in found] == ["a_song", "b_song"]
+    os.makedirs(tmp_path / "flat")
+    audio_io.write_wav_pcm16(str(tmp_path / "flat" / "x.wav"), y, 8192)
+    assert separate.find_songs(str(tmp_path / "flat")) == [("x", str(tmp_path / "flat" / "x.wav"))]
+    a = separate.build_parser().parse_args(["--model_path", "m", "--src", "s", "--tar", "t"])
+    assert (a.vocal_solo, a.sr, a.emit_npy) == (1, 8192, "")
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SvsError):
+            separate.main(["--model_path", "m", "--src", str(tmp_path / "songs"), "--tar", str(tmp_path / "out")])
+
+
 def test_patch_table_edge_cases():
     from svs_unet_pytorch_b200 import pipeline
     offs, valid, song = pipeline.patch_table([1, 127, 128, 129, 256], np.array([0, 1, 128, 256, 385, 641]))
