@@ -13,30 +13,32 @@ namespace svs {
 
 constexpr int kPatchF = 512, kPatchT = 128, kTileF = 32;
 
-// grid (16, n): block = 32 frequencies x 128 frames of one patch
+// grid (4, n): block = 32 consecutive frames x all 513 bins of one patch.  The 32 frame rows are one contiguous
+// 65.7 KB run of the spectrogram, so the reads are perfectly coalesced (a 32-frequency tile read 128-byte pieces of
+// 2,052-byte rows: 5 sectors per 4 used); the transposed write-out is one 128-byte line per warp store.
+constexpr int kGatherT = 32;
+constexpr int kGatherPitch = SVS_N_BINS;                       // 513 = 1 mod 32: column reads are conflict free
+constexpr size_t kGatherSmemBytes = sizeof(float) * kGatherT * kGatherPitch;
+
 __global__ void __launch_bounds__(256)
 patches_gather_kernel(const float* __restrict__ spec, const int64_t* __restrict__ patch_off,
                       const int32_t* __restrict__ in_frames, const float* __restrict__ norm,
                       float* __restrict__ patches) {
-  __shared__ float tile[kPatchT][kTileF + 1];
-  const int p = blockIdx.y, f0 = blockIdx.x * kTileF;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  extern __shared__ float tile[];                              // [32 frames][513 bins]
+  const int p = blockIdx.y, t0 = blockIdx.x * kGatherT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int valid = in_frames ? in_frames[p] : kPatchT;
   float nrm = norm ? norm[p] : 1.0f;
   if (nrm == 0.0f) nrm = 1.0f;                                  // reference data.py:85
-  const float* src = spec + patch_off[p] + f0 + tx;
-#pragma unroll 4
-  for (int t = ty; t < kPatchT; t += 8)
-    tile[t][tx] = t < valid ? __ldg(src + static_cast<int64_t>(t) * SVS_N_BINS) / nrm : 0.0f;   // inference.py:90-92
+  // patch_off points at bin 1 of the patch's first frame; row t of the tile starts at that frame's DC bin
+  const float* src = spec + patch_off[p] - 1 + static_cast<int64_t>(t0) * SVS_N_BINS;
+  const int rows = min(kGatherT, max(0, valid - t0));           // frames >= valid are zero padding (inference.py:90-92)
+  for (int i = threadIdx.x; i < rows * SVS_N_BINS; i += 256) tile[i] = __ldg(src + i);
   __syncthreads();
-  float* dst = patches + (static_cast<int64_t>(p) * kPatchF + f0) * kPatchT;
-  // a warp writes 32 consecutive frames of one frequency row (128 bytes); the padded tile keeps the transposed
-  // shared-memory reads conflict free
+  float* dst = patches + static_cast<int64_t>(p) * kPatchF * kPatchT + t0 + lane;
 #pragma unroll 4
-  for (int i = ty; i < kTileF * 4; i += 8) {
-    const int f = i >> 2, t = 32 * (i & 3) + tx;
-    dst[f * kPatchT + t] = tile[t][f];
-  }
+  for (int f = warp; f < kPatchF; f += 8)
+    dst[f * kPatchT] = lane < rows ? tile[lane * kGatherPitch + f + 1] / nrm : 0.0f;
 }
 
 __global__ void __launch_bounds__(256)
@@ -68,7 +70,9 @@ extern "C" int svs_patches_gather(const float* spec, const int64_t* patch_off, c
   SVS_REQUIRE(spec && patch_off && patches, "svs_patches_gather: null pointer");
   SVS_REQUIRE(n >= 0 && n <= 65535, "svs_patches_gather: n must be in [0, 65535]");
   if (n == 0) return SVS_OK;
-  patches_gather_kernel<<<dim3(kPatchF / kTileF, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  SVS_CUDA_TRY(cudaFuncSetAttribute(patches_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kGatherSmemBytes)));
+  patches_gather_kernel<<<dim3(kPatchT / kGatherT, n), 256, kGatherSmemBytes, static_cast<cudaStream_t>(stream)>>>(
       spec, patch_off, in_frames, norm, patches);
   SVS_CHECK_LAUNCH("patches_gather_kernel");
   return SVS_OK;
