@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SVS_ABI_VERSION 1
+#define SVS_ABI_VERSION 2
 
 /* geometry of the path (reference config.py:47-51) */
 #define SVS_N_FFT        1024
@@ -79,6 +79,13 @@ int svs_stft_mag_phase(const float* audio, const int64_t* sample_off, const int6
                        int n_songs, int64_t max_frames, float* mag, float* phase, float* song_max,
                        void* stream);
 
+/* The same transform straight from the PCM_16 samples of the .wav file (reference data.py:78: librosa.load of a
+ * 16-bit file is int16 / 32768, applied here inside the load): `audio` is device int16, song s =
+ * audio[sample_off[s] .. sample_off[s+1]).  Halves the host -> device bytes of the end-to-end path. */
+int svs_stft_mag_phase_pcm16(const int16_t* audio, const int64_t* sample_off, const int64_t* frame_off,
+                             int n_songs, int64_t max_frames, float* mag, float* phase, float* song_max,
+                             void* stream);
+
 /* librosa.stft alone (reference data.py:79,100): raw complex64 spectrum [total_frames][513][2]. */
 int svs_stft_complex(const float* audio, const int64_t* sample_off, const int64_t* frame_off,
                      int n_songs, int64_t max_frames, float* spec, void* stream);
@@ -105,6 +112,13 @@ int svs_istft_ola(const float* mag, const float* phase, const int64_t* frame_off
 /* y <- y / peak * target where peak > 0 (reference data.py:163-164, target 0.9). */
 int svs_wave_peak_normalize(float* wave, const int64_t* wave_off, const float* song_peak,
                             int n_songs, int64_t total_samples, float target, void* stream);
+
+/* The normalisation above fused with the PCM_16 quantiser of `sf.write(path, y, sr)` at reference data.py:166
+ * (libsndfile: lrintf(y * 0x7FFF)): pcm_out[i] = rint(wave[i] / peak * target * 32767), int16, same offsets as
+ * `wave` (which is left untouched).  Halves the device -> host bytes of the end-to-end path. */
+int svs_wave_peak_normalize_pcm16(const float* wave, const int64_t* wave_off, const float* song_peak,
+                                  int n_songs, int64_t total_samples, float target, int16_t* pcm_out,
+                                  void* stream);
 
 /* ------------------------------------------------------------------ patch staging (I2, I4)
  * Replaces the per-patch segment / zero-pad / contiguous copy of reference inference.py:74-97 and the
@@ -218,9 +232,12 @@ int svs_unet_train_backward(const svs_train_layer layers[12], const float* mix, 
 
 /* Fused loss of reference train.py:275-283 and its gradient w.r.t. the mask:
  *   L = mean|m*x - v| (+ mean|(1-m)*x - max(x - v, 0)| when two_term)      n = number of elements
- * loss_out: device float32 [3] = {total, vocal term, accompaniment term}; grad_mask_out may be NULL. */
+ * loss_out: device float32 [3] = {total, vocal term, accompaniment term}; grad_mask_out may be NULL.
+ * scratch: device float32 [SVS_L1_SCRATCH_FLOATS] owned by the caller (per-block partial sums of the two-stage,
+ * fixed-order reduction; concurrent calls on different streams need different scratch buffers). */
+#define SVS_L1_SCRATCH_FLOATS 2048
 int svs_l1_masked_loss(const float* mask, const float* mix, const float* voc, int64_t n, int two_term,
-                       float grad_scale, float* loss_out, float* grad_mask_out, void* stream);
+                       float grad_scale, float* loss_out, float* grad_mask_out, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

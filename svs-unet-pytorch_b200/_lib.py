@@ -19,6 +19,8 @@ FLAG_APPLY_MASK = 1
 FLAG_INVERT = 2
 
 N_FFT, HOP, N_BINS, PATCH_BINS, PATCH_FRAMES = 1024, 768, 513, 512, 128
+ABI_VERSION = 2
+L1_SCRATCH_FLOATS = 2048
 
 
 class ConvParams(Structure):
@@ -51,11 +53,13 @@ _SIGNATURES = [
     ("svs_last_error", c_char_p, []),
     ("svs_device_check", c_int, [c_int]),
     ("svs_stft_mag_phase", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("svs_stft_mag_phase_pcm16", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("svs_stft_complex", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     ("svs_magphase", c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     ("svs_spec_normalize", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     ("svs_istft_ola", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     ("svs_wave_peak_normalize", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p]),
+    ("svs_wave_peak_normalize_pcm16", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p, c_void_p]),
     ("svs_patches_gather", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     ("svs_patches_scatter", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     ("svs_unet_plan_create", c_int, [POINTER(ConvParams), c_int, c_void_p, POINTER(c_void_p)]),
@@ -75,7 +79,7 @@ _SIGNATURES = [
     ("svs_unet_train_backward", c_int, [POINTER(TrainLayer), c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                         c_void_p]),
     ("svs_l1_masked_loss", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_void_p]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
@@ -101,7 +105,7 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)          # AttributeError = ABI mismatch, fail loudly
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.svs_version() != 1:
+        if lib.svs_version() != ABI_VERSION:
             raise SvsError("libsvs_b200.so ABI version mismatch")
         _lib = lib
         return _lib
@@ -140,14 +144,17 @@ def check_device(device: torch.device):
 
 def stft_mag_phase_raw(audio, sample_off, frame_off, n_songs, max_frames, total_frames, want_phase=True,
                        want_max=True):
-    require_cuda(audio, "audio", torch.float32)
+    require_cuda(audio, "audio")
+    if audio.dtype not in (torch.float32, torch.int16):
+        raise SvsError(f"audio must be float32 or int16 PCM, got {audio.dtype}")
     check_device(audio.device)
     dev = audio.device
     mag = torch.empty((total_frames, N_BINS), dtype=torch.float32, device=dev)
     phase = torch.empty((total_frames, N_BINS, 2), dtype=torch.float32, device=dev) if want_phase else None
     smax = torch.empty((n_songs,), dtype=torch.float32, device=dev) if want_max else None
+    fn = load().svs_stft_mag_phase if audio.dtype == torch.float32 else load().svs_stft_mag_phase_pcm16
     with torch.cuda.device(dev):
-        check(load().svs_stft_mag_phase(audio.data_ptr(), sample_off.data_ptr(), frame_off.data_ptr(), n_songs,
+        check(fn(audio.data_ptr(), sample_off.data_ptr(), frame_off.data_ptr(), n_songs,
                                         max_frames, mag.data_ptr(),
                                         phase.data_ptr() if phase is not None else None,
                                         smax.data_ptr() if smax is not None else None, stream_ptr(dev)),
@@ -205,6 +212,17 @@ def wave_peak_normalize_raw(wave, wave_off, peak, n_songs, target=0.9):
                                              wave.numel(), target, stream_ptr(wave.device)),
               "svs_wave_peak_normalize")
     return wave
+
+
+def wave_peak_normalize_pcm16_raw(wave, wave_off, peak, n_songs, target=0.9, out=None):
+    """float32 waveforms -> int16 PCM with the 0.9 / peak normalisation fused (reference data.py:162-166)."""
+    if out is None:
+        out = torch.empty(wave.shape, dtype=torch.int16, device=wave.device)
+    with torch.cuda.device(wave.device):
+        check(load().svs_wave_peak_normalize_pcm16(wave.data_ptr(), wave_off.data_ptr(), peak.data_ptr(), n_songs,
+                                                   wave.numel(), target, out.data_ptr(), stream_ptr(wave.device)),
+              "svs_wave_peak_normalize_pcm16")
+    return out
 
 
 def patches_gather_raw(spec, patch_off, in_frames, norm, out=None):
@@ -287,13 +305,22 @@ class UNetPlan:
             pass
 
     def workspace(self, batch: int) -> torch.Tensor:
-        ws = self._ws.get(batch)
-        if ws is None:
-            nbytes = load().svs_unet_workspace_bytes(self.handle, batch)
-            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
-            off = (-raw.data_ptr()) % 1024
-            ws = raw[off:off + nbytes]
-            self._ws = {batch: ws}        # keep only the last size
+        """Activation workspace for `batch` patches on the CURRENT stream.  svs_unet_forward writes every concat
+        buffer into it, so two forwards in flight on different streams must not share one: the cache is keyed by
+        stream (each stream keeps the workspace of its last batch size).  A workspace is only ever used on the
+        stream it was allocated under, so dropping it hands the block back to the caching allocator's pool of that
+        same stream and any re-use is stream-ordered after the kernels that still read it."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        hit = self._ws.get(key)
+        if hit is not None and hit[0] == batch:
+            return hit[1]
+        nbytes = load().svs_unet_workspace_bytes(self.handle, batch)
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+        off = (-raw.data_ptr()) % 1024
+        ws = raw[off:off + nbytes]
+        if hit is None and len(self._ws) >= 16:                       # bound the number of per-stream workspaces
+            self._ws.pop(next(iter(self._ws)))
+        self._ws[key] = (batch, ws)
         return ws
 
     def launch_count(self, batch: int) -> int:

@@ -71,8 +71,11 @@ def load(path: str, sr: int, mono: bool = True) -> np.ndarray:
 
 def write_wav_pcm16(path: str, y: np.ndarray, sr: int):
     """soundfile.write(path, y, sr) default for .wav: PCM_16 (reference data.py:166)."""
-    y = np.asarray(y, dtype=np.float64)
-    q = np.clip(np.rint(y * 32768.0), -32768, 32767).astype("<i2")   # libsndfile float->short scaling
+    y = np.asarray(y)
+    if y.dtype == np.int16:                                          # already quantised on the device
+        q = y.astype("<i2")
+    else:                                                            # libsndfile f2les_array: lrintf(x * 0x7FFF)
+        q = np.clip(np.rint(y.astype(np.float64) * 32767.0), -32768, 32767).astype("<i2")
     body = q.tobytes()
     with open(path, "wb") as f:
         f.write(b"RIFF" + struct.pack("<I", 36 + len(body)) + b"WAVE")

@@ -1,16 +1,21 @@
-"""Builds libsvs_b200.so in-tree with nvcc for sm_100a (the only supported target)."""
+"""Builds libsvs_b200.so in-tree with nvcc for sm_100a (the only supported target).
+
+Every csrc/*.cu is compiled to an object under build/ (in parallel, only when it or a header is newer than the
+object) and the objects are linked into libsvs_b200.so next to this file."""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libsvs_b200.so")
-SOURCES = ["common.cu", "stft.cu", "istft.cu", "patches.cu", "conv_direct.cu", "conv_tc.cu", "conv_tc_cluster.cu", "conv1_tc.cu", "conv1_zc.cu", "zc_conv.cu", "deconv6_tc.cu", "unet.cu", "train.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def _nvcc() -> str:
@@ -18,6 +23,16 @@ def _nvcc() -> str:
         if cand and os.path.exists(cand):
             return cand
     raise RuntimeError("nvcc not found; libsvs_b200.so cannot be built")
+
+
+def sources() -> list[str]:
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _headers_mtime() -> float:
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(INCLUDE, "svs_b200.h"))
+    return max(os.path.getmtime(h) for h in hs)
 
 
 def needs_build() -> bool:
@@ -31,17 +46,33 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + srcs
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_t = _headers_mtime()
+    flags = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+        flags += ["-Xptxas", "-v"]
+
+    def compile_one(src: str):
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src[:-3] + ".o")
+        if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), hdr_t):
+            return o, ""
+        proc = subprocess.run([nvcc] + flags + ["-c", s, "-o", o], capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + proc.stdout + proc.stderr)
+        return o, proc.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    if verbose:
+        for _, log in results:
+            if log:
+                print(log)
+    objs = [o for o, _ in results]
+    proc = subprocess.run([nvcc] + ARCH + ["-shared", "-o", LIB_PATH] + objs, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+        raise RuntimeError("nvcc link failed:\n" + proc.stdout + proc.stderr)
     return LIB_PATH
 
 

@@ -641,13 +641,19 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   CUtensorMap ta;
   {
     std::lock_guard<std::mutex> lock(mu);
-    if (t.tmap_a_base != ws.buf[g.in_buf] || t.tmap_a_batch != batch) {
-      int rc = make_tmap_a(t, g, ws.buf[g.in_buf], batch, es, tf32, &t.tmap_a);
+    int hit = -1;
+    for (int i = 0; i < TcLayer::kTmapCache; ++i)
+      if (t.tmap_a_base[i] == ws.buf[g.in_buf] && t.tmap_a_batch[i] == batch) hit = i;
+    if (hit < 0) {
+      hit = t.tmap_a_next;
+      t.tmap_a_next = (t.tmap_a_next + 1) % TcLayer::kTmapCache;
+      t.tmap_a_base[hit] = nullptr;
+      int rc = make_tmap_a(t, g, ws.buf[g.in_buf], batch, es, tf32, &t.tmap_a[hit]);
       if (rc != SVS_OK) return rc;
-      t.tmap_a_base = ws.buf[g.in_buf];
-      t.tmap_a_batch = batch;
+      t.tmap_a_base[hit] = ws.buf[g.in_buf];
+      t.tmap_a_batch[hit] = batch;
     }
-    ta = t.tmap_a;
+    ta = t.tmap_a[hit];
   }
   TcParams p{};
   p.chunks = t.d_chunks;

@@ -184,6 +184,39 @@ wave_peak_normalize_kernel(float* __restrict__ wave, const int64_t* __restrict__
   }
 }
 
+// The PCM_16 writer of reference data.py:166 (soundfile.write -> libsndfile f2les_array: lrintf(x * 0x7FFF)) fused
+// with the 0.9 / peak normalisation of data.py:163-164: one pass, 4 bytes read + 2 bytes written per sample, and the
+// download is half the size of the float waveform.
+__global__ void __launch_bounds__(256)
+wave_peak_normalize_pcm16_kernel(const float* __restrict__ wave, const int64_t* __restrict__ wave_off,
+                                 const float* __restrict__ song_peak, float target, int16_t* __restrict__ out) {
+  const int s = blockIdx.y;
+  const float pk = song_peak[s];
+  const bool scale = pk > 0.0f;                              // data.py:163: silent songs stay as they are
+  const int64_t a = wave_off[s], n = wave_off[s + 1] - a;
+  const float* w = wave + a;
+  int16_t* o = out + a;
+  auto q = [&](float v) {
+    if (scale) v = v / pk * target;                          // data.py:164, same expression as the float pass
+    const float r = fminf(fmaxf(v * 32767.0f, -32768.0f), 32767.0f);
+    return static_cast<int16_t>(__float2int_rn(r));
+  };
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    short4* o4 = reinterpret_cast<short4*>(o);
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 v = __ldcs(&w4[i]);
+      o4[i] = make_short4(q(v.x), q(v.y), q(v.z), q(v.w));
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) o[i] = q(w[i]);
+  } else {
+    for (int64_t i = tid; i < n; i += stride) o[i] = q(w[i]);
+  }
+}
+
 }  // namespace svs
 
 extern "C" int svs_istft_ola(const float* mag, const float* phase, const int64_t* frame_off,
@@ -220,5 +253,20 @@ extern "C" int svs_wave_peak_normalize(float* wave, const int64_t* wave_off, con
   wave_peak_normalize_kernel<<<dim3(per_song, n_songs), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       wave, wave_off, song_peak, target);
   SVS_CHECK_LAUNCH("wave_peak_normalize_kernel");
+  return SVS_OK;
+}
+
+extern "C" int svs_wave_peak_normalize_pcm16(const float* wave, const int64_t* wave_off, const float* song_peak,
+                                             int n_songs, int64_t total_samples, float target, int16_t* pcm_out,
+                                             void* stream) {
+  using namespace svs;
+  SVS_REQUIRE(wave && wave_off && song_peak && pcm_out, "svs_wave_peak_normalize_pcm16: null pointer");
+  SVS_REQUIRE(n_songs > 0 && n_songs <= 65535 && total_samples >= 0, "svs_wave_peak_normalize_pcm16: bad sizes");
+  if (total_samples == 0) return SVS_OK;
+  int per_song = (148 * 8 + n_songs - 1) / n_songs;
+  if (per_song < 4) per_song = 4;
+  wave_peak_normalize_pcm16_kernel<<<dim3(per_song, n_songs), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      wave, wave_off, song_peak, target, pcm_out);
+  SVS_CHECK_LAUNCH("wave_peak_normalize_pcm16_kernel");
   return SVS_OK;
 }

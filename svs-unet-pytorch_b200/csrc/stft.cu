@@ -33,9 +33,11 @@ __device__ __forceinline__ void mag_phase(float2 x, float& m, float2& ph) {
   }
 }
 
-template <bool kComplexOut>
+// InT = float (librosa.load's output) or int16_t (the PCM_16 samples of the .wav itself, reference data.py:78:
+// libsndfile / librosa.load scale them by 1/32768 — fused into the load, so the upload is 2 bytes per sample)
+template <bool kComplexOut, typename InT>
 __global__ void __launch_bounds__(kStftThreads, 3)
-stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict__ sample_off,
+stft_mag_phase_kernel(const InT* __restrict__ audio, const int64_t* __restrict__ sample_off,
                       const int64_t* __restrict__ frame_off, float* __restrict__ mag,
                       float2* __restrict__ phase, float* __restrict__ song_max,
                       const float2* __restrict__ tw1024, const float* __restrict__ hann) {
@@ -48,8 +50,8 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
   const int t_end = min(n_frames, t_begin + kStftFramesPerCta);
   const int64_t s0 = sample_off[song];
   const int len = static_cast<int>(sample_off[song + 1] - s0);
-  const float* __restrict__ y = audio + s0;
-  const bool vec2 = (reinterpret_cast<uintptr_t>(y) & 7) == 0;      // frame starts are even sample offsets
+  const InT* __restrict__ y = audio + s0;
+  const bool vec2 = (reinterpret_cast<uintptr_t>(y) & (2 * sizeof(InT) - 1)) == 0;   // frame starts are even sample offsets
 
   const int group = threadIdx.x >> 6;
   const int j = threadIdx.x & 63;
@@ -79,11 +81,22 @@ stft_mag_phase_kernel(const float* __restrict__ audio, const int64_t* __restrict
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) {
       const int i0 = base + 2 * (j + 64 * n1);
-      if (vec2 && i0 >= 0 && i0 + 1 < len) {
-        raw[n1] = __ldg(reinterpret_cast<const float2*>(y + i0));
+      if constexpr (sizeof(InT) == 4) {
+        if (vec2 && i0 >= 0 && i0 + 1 < len) {
+          raw[n1] = __ldg(reinterpret_cast<const float2*>(y + i0));
+        } else {
+          raw[n1].x = (i0 >= 0 && i0 < len) ? __ldg(&y[i0]) : 0.0f;
+          raw[n1].y = (i0 + 1 >= 0 && i0 + 1 < len) ? __ldg(&y[i0 + 1]) : 0.0f;
+        }
       } else {
-        raw[n1].x = (i0 >= 0 && i0 < len) ? __ldg(&y[i0]) : 0.0f;
-        raw[n1].y = (i0 + 1 >= 0 && i0 + 1 < len) ? __ldg(&y[i0 + 1]) : 0.0f;
+        constexpr float kScale = 1.0f / 32768.0f;
+        if (vec2 && i0 >= 0 && i0 + 1 < len) {
+          const short2 q = __ldg(reinterpret_cast<const short2*>(y + i0));
+          raw[n1] = make_float2(static_cast<float>(q.x) * kScale, static_cast<float>(q.y) * kScale);
+        } else {
+          raw[n1].x = (i0 >= 0 && i0 < len) ? static_cast<float>(__ldg(&y[i0])) * kScale : 0.0f;
+          raw[n1].y = (i0 + 1 >= 0 && i0 + 1 < len) ? static_cast<float>(__ldg(&y[i0 + 1])) * kScale : 0.0f;
+        }
       }
     }
   };
@@ -180,24 +193,39 @@ __global__ void spec_normalize_kernel(float* __restrict__ mag, const int64_t* __
 
 }  // namespace svs
 
-extern "C" int svs_stft_mag_phase(const float* audio, const int64_t* sample_off, const int64_t* frame_off,
-                                  int n_songs, int64_t max_frames, float* mag, float* phase,
-                                  float* song_max, void* stream) {
-  using namespace svs;
-  SVS_REQUIRE(audio && sample_off && frame_off && mag, "svs_stft_mag_phase: null pointer");
-  SVS_REQUIRE(n_songs > 0 && n_songs <= 65535, "svs_stft_mag_phase: n_songs must be in [1, 65535]");
-  SVS_REQUIRE(max_frames > 0, "svs_stft_mag_phase: max_frames must be positive");
+namespace svs {
+template <typename InT>
+static int launch_stft(const InT* audio, const int64_t* sample_off, const int64_t* frame_off, int n_songs,
+                       int64_t max_frames, float* mag, float* phase, float* song_max, void* stream, const char* what) {
+  if (!(audio && sample_off && frame_off && mag)) return fail(SVS_ERR_INVALID_ARG, std::string(what) + ": null pointer");
+  if (!(n_songs > 0 && n_songs <= 65535)) return fail(SVS_ERR_INVALID_ARG, std::string(what) + ": n_songs must be in [1, 65535]");
+  if (!(max_frames > 0)) return fail(SVS_ERR_INVALID_ARG, std::string(what) + ": max_frames must be positive");
   SpectralTables tabs;
   int rc = get_spectral_tables(&tabs);
   if (rc != SVS_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (song_max) SVS_CUDA_TRY(cudaMemsetAsync(song_max, 0, sizeof(float) * n_songs, st));
   dim3 grid(static_cast<unsigned>((max_frames + kStftFramesPerCta - 1) / kStftFramesPerCta), n_songs);
-  stft_mag_phase_kernel<false><<<grid, kStftThreads, 0, st>>>(audio, sample_off, frame_off, mag,
-                                                              reinterpret_cast<float2*>(phase), song_max,
-                                                              tabs.tw1024, tabs.hann);
+  stft_mag_phase_kernel<false, InT><<<grid, kStftThreads, 0, st>>>(audio, sample_off, frame_off, mag,
+                                                                   reinterpret_cast<float2*>(phase), song_max,
+                                                                   tabs.tw1024, tabs.hann);
   SVS_CHECK_LAUNCH("stft_mag_phase_kernel");
   return SVS_OK;
+}
+}  // namespace svs
+
+extern "C" int svs_stft_mag_phase(const float* audio, const int64_t* sample_off, const int64_t* frame_off,
+                                  int n_songs, int64_t max_frames, float* mag, float* phase,
+                                  float* song_max, void* stream) {
+  return svs::launch_stft(audio, sample_off, frame_off, n_songs, max_frames, mag, phase, song_max, stream,
+                          "svs_stft_mag_phase");
+}
+
+extern "C" int svs_stft_mag_phase_pcm16(const int16_t* audio, const int64_t* sample_off, const int64_t* frame_off,
+                                        int n_songs, int64_t max_frames, float* mag, float* phase,
+                                        float* song_max, void* stream) {
+  return svs::launch_stft(audio, sample_off, frame_off, n_songs, max_frames, mag, phase, song_max, stream,
+                          "svs_stft_mag_phase_pcm16");
 }
 
 extern "C" int svs_stft_complex(const float* audio, const int64_t* sample_off, const int64_t* frame_off,
@@ -210,7 +238,7 @@ extern "C" int svs_stft_complex(const float* audio, const int64_t* sample_off, c
   int rc = get_spectral_tables(&tabs);
   if (rc != SVS_OK) return rc;
   dim3 grid(static_cast<unsigned>((max_frames + kStftFramesPerCta - 1) / kStftFramesPerCta), n_songs);
-  stft_mag_phase_kernel<true><<<grid, kStftThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  stft_mag_phase_kernel<true, float><<<grid, kStftThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       audio, sample_off, frame_off, nullptr, reinterpret_cast<float2*>(spec), nullptr, tabs.tw1024, tabs.hann);
   SVS_CHECK_LAUNCH("stft_complex_kernel");
   return SVS_OK;

@@ -509,7 +509,7 @@ extern "C" size_t svs_unet_train_workspace_bytes(int batch) {
 static int check_train_args(const svs_train_layer layers[12], const void* mix, int batch, void* workspace,
                             size_t workspace_bytes) {
   SVS_REQUIRE(layers && mix && workspace, "svs_unet_train: null pointer");
-  SVS_REQUIRE(batch > 1, "svs_unet_train: batch must be > 1 (batch-statistic BatchNorm)");
+  SVS_REQUIRE(batch >= 1, "svs_unet_train: batch must be positive");   // B = 1 is fine: N = B*H*W >= 16 per channel
   SVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "svs_unet_train: workspace must be 256-byte aligned");
   for (int i = 0; i < 12; ++i) {
     SVS_REQUIRE(layers[i].weight && layers[i].bias, "svs_unet_train: weight/bias missing");
@@ -670,19 +670,14 @@ extern "C" int svs_unet_train_backward(const svs_train_layer layers[12], const f
 }
 
 extern "C" int svs_l1_masked_loss(const float* mask, const float* mix, const float* voc, int64_t n, int two_term,
-                                  float grad_scale, float* loss_out, float* grad_mask_out, void* stream) {
-  SVS_REQUIRE(mask && mix && voc && loss_out && n > 0, "svs_l1_masked_loss: bad arguments");
+                                  float grad_scale, float* loss_out, float* grad_mask_out, float* scratch,
+                                  void* stream) {
+  SVS_REQUIRE(mask && mix && voc && loss_out && scratch && n > 0, "svs_l1_masked_loss: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // partial sums live at the tail of loss_out? No: the caller provides only 3 floats, so use a static
-  // per-device scratch allocated once.
-  static float* scratch[64] = {};
-  int dev = 0;
-  SVS_CUDA_TRY(cudaGetDevice(&dev));
-  if (!scratch[dev]) SVS_CUDA_TRY(cudaMalloc(&scratch[dev], sizeof(float) * 2 * 1024));
   l1_loss_kernel<<<1024, 256, 0, st>>>(mask, mix, voc, static_cast<size_t>(n), two_term, grad_scale / static_cast<float>(n),
-                                       scratch[dev], grad_mask_out);
+                                       scratch, grad_mask_out);
   SVS_CHECK_LAUNCH("l1_loss_kernel");
-  l1_loss_finalize_kernel<<<1, 1, 0, st>>>(scratch[dev], 1024, static_cast<double>(n), loss_out);
+  l1_loss_finalize_kernel<<<1, 1, 0, st>>>(scratch, 1024, static_cast<double>(n), loss_out);
   SVS_CHECK_LAUNCH("l1_loss_finalize_kernel");
   return SVS_OK;
 }

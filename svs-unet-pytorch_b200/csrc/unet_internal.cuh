@@ -89,10 +89,13 @@ struct TcLayer {
   CUtensorMap tmap_b[4];             // per phase, 2-D [Cout][K]
   bool has_wide = false;             // deep layers also carry a 256-row box: large batches use 128 x 256 tiles
   CUtensorMap tmap_b_wide[4];
-  // A-operand tensor map depends on (workspace, batch): cached for the last pair seen
-  mutable CUtensorMap tmap_a;
-  mutable const void* tmap_a_base = nullptr;
-  mutable int tmap_a_batch = -1;
+  // A-operand tensor map depends on (workspace, batch): a small round-robin cache (one workspace per stream and
+  // batch size is in flight when several streams share a plan)
+  static constexpr int kTmapCache = 8;
+  mutable CUtensorMap tmap_a[kTmapCache];
+  mutable const void* tmap_a_base[kTmapCache] = {};
+  mutable int tmap_a_batch[kTmapCache] = {};
+  mutable int tmap_a_next = 0;
 };
 
 // ---- zero-copy tcgen05 layers (zc_conv.cu) -------------------------------------------------------

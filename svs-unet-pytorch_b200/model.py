@@ -133,7 +133,11 @@ class UNet(nn.Module):
 
     # ------------------------------------------------------------------ forward (model.py:169-201)
     def forward(self, mix):
-        """mix (B,1,512,128) float32 on CUDA -> soft mask (B,1,512,128) float32."""
+        """mix (B,1,512,128) float32 on CUDA -> soft mask (B,1,512,128) float32.
+
+        In ``train()`` mode the mask carries an autograd edge to every parameter; the activations the backward
+        needs are kept in one per-model workspace, so only the MOST RECENT train-mode forward can be
+        back-propagated (a stale ``backward()`` raises; the reference's plain autograd has no such limit)."""
         _lib.require_cuda(mix, "mix")
         if self.training:
             from . import training

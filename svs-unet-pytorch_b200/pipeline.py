@@ -63,9 +63,10 @@ class Separator:
 
     @torch.no_grad()
     def separate_batch(self, batch: SongBatch, vocal_solo: bool = True, peak_normalize: bool = True,
-                       return_spec: bool = False):
+                       return_spec: bool = False, pcm16: bool = False):
         """SongBatch (device audio) -> (wave [total_wave] f32 device, peak [n_songs]); optionally also the
-        normalised mixture spectrogram, the phase and the masked spectrogram ([F,513] layouts)."""
+        normalised mixture spectrogram, the phase and the masked spectrogram ([F,513] layouts).  ``pcm16``: the
+        waveform comes back as int16 PCM (0.9 peak normalisation + the PCM_16 quantiser of data.py:166 in one pass)."""
         plan = self.model.plan()
         mag, phase, smax = batch.stft()
         dev = mag.device
@@ -95,7 +96,7 @@ class Separator:
                 iv = _lib.PatchView(mag.data_ptr(), d_off[a:b].data_ptr(), 0, 1, N_BINS)
                 ov = _lib.PatchView(out_mag.data_ptr(), d_off[a:b].data_ptr(), 0, 1, N_BINS)
                 plan.forward_views(iv, ov, d_valid[a:b], b - a, flags)
-        wave, peak = batch.istft(out_mag, phase, peak_normalize=peak_normalize)   # data.py:159-164
+        wave, peak = batch.istft(out_mag, phase, peak_normalize=peak_normalize, pcm16=pcm16)   # data.py:159-166
         if return_spec:
             return wave, peak, mag, phase, out_mag
         return wave, peak
@@ -125,9 +126,12 @@ class SongStreamer:
 
     @torch.no_grad()
     def run(self, host_audio: torch.Tensor, lengths, host_wave: torch.Tensor):
-        """host_audio: pinned float32 [sum(lengths)] (songs back to back); host_wave: pinned float32
-        [sum(768 * (len // 768))] receiving the separated songs back to back.  Returns per-song wave lengths."""
+        """host_audio: pinned float32 — or int16 PCM — [sum(lengths)] (songs back to back); host_wave: pinned float32
+        — or int16 PCM — [sum(768 * (len // 768))] receiving the separated songs back to back.  int16 on either side
+        is the reference's real file boundary (PCM_16 .wav in, data.py:78; PCM_16 .wav out, data.py:166) and halves
+        the PCIe bytes of that direction.  Returns per-song wave lengths."""
         n = len(lengths)
+        pcm_out = host_wave.dtype == torch.int16
         cur = torch.cuda.current_stream(self.dev)
         for s in self.streams:
             s.wait_stream(cur)
@@ -140,7 +144,7 @@ class SongStreamer:
             with torch.cuda.stream(st):
                 audio = host_audio[in_off:in_off + n_in].to(self.dev, non_blocking=True)
                 batch = SongBatch(audio, lens)
-                wave, _ = self.sep.separate_batch(batch, self.vocal_solo, True)
+                wave, _ = self.sep.separate_batch(batch, self.vocal_solo, True, pcm16=pcm_out)
                 host_wave[out_off:out_off + batch.total_wave].copy_(wave, non_blocking=True)
                 keep.append((audio, wave))
             wave_lengths += batch.wave_lengths
@@ -200,3 +204,70 @@ class PatchStreamer:
         cur.wait_stream(self.s_out)
         cur.wait_stream(self.s_cmp)
         cur.wait_stream(self.s_in)
+
+
+class CopyCeiling:
+    """The PCIe ceiling of PatchStreamer / SongStreamer on this box: the same pinned-host <-> device copies with no
+    kernels in between, H2D and D2H on two streams (one DMA engine per direction).  bench.py runs it on every rank
+    at once, so the figure includes whatever the ranks share (root complex, host memory controllers)."""
+
+    def __init__(self, device, nbytes: int):
+        self.dev = device
+        self.buf_in = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf_out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.s_in, self.s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def run(self, host_in: torch.Tensor, host_out: torch.Tensor, steps: int):
+        hin = host_in.view(-1).view(torch.uint8)[: self.buf_in.numel()]
+        hout = host_out.view(-1).view(torch.uint8)[: self.buf_out.numel()]
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_in.wait_stream(cur)
+        self.s_out.wait_stream(cur)
+        for _ in range(steps):
+            with torch.cuda.stream(self.s_in):
+                self.buf_in.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(self.s_out):
+                hout.copy_(self.buf_out, non_blocking=True)
+        cur.wait_stream(self.s_in)
+        cur.wait_stream(self.s_out)
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pins this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, BEFORE pinned host buffers
+    are allocated, so that they are first-touched on that node: with eight ranks on one socket's memory every copy
+    of the other socket's four GPUs crosses the inter-socket link.  Best effort; returns what it did."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        index = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if ids and all(v.isdigit() for v in ids) and local_rank < len(ids):
+            index = int(ids[local_rank])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                               # nvml: 00000000:1b:00.0 -> sysfs 0000:1b:00.0
+            bus = bus[4:]
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(base + "/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        orig = os.sched_getaffinity(0)
+        cpus &= orig
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus), original_affinity=sorted(orig))
+    except Exception as e:                                            # no nvml / sysfs: run unbound
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info

@@ -36,8 +36,10 @@ class SongBatch:
     _offset_cache: dict = {}
 
     def __init__(self, audio: torch.Tensor, lengths: list[int]):
-        _lib.require_cuda(audio, "audio", torch.float32)
-        self.audio = audio
+        _lib.require_cuda(audio, "audio")
+        if audio.dtype not in (torch.float32, torch.int16):
+            raise _lib.SvsError(f"audio must be float32 samples or int16 PCM, got {audio.dtype}")
+        self.audio = audio                                                # int16: the /32768 of librosa.load is fused into K1
         self.lengths = [int(n) for n in lengths]
         self.n_songs = len(self.lengths)
         self.frames = [1 + n // HOP_SIZE for n in self.lengths]           # librosa: 1 + len // hop
@@ -90,12 +92,20 @@ class SongBatch:
         """spec /= norm per song (reference data.py:105); in place."""
         return _lib.spec_normalize_raw(mag, self.frame_off, norm, self.n_songs)
 
-    def istft(self, mag: torch.Tensor, phase: torch.Tensor, peak_normalize: bool = False):
+    def istft(self, mag: torch.Tensor, phase: torch.Tensor, peak_normalize: bool = False, pcm16: bool = False):
         """-> (wave [total_wave] f32, song_peak [n_songs] f32).  Optional 0.9 peak normalisation
-        (reference data.py:162-164)."""
+        (reference data.py:162-164).  ``pcm16=True`` returns int16 PCM instead: the normalisation fused with the
+        PCM_16 quantiser of ``sf.write`` (data.py:166), i.e. the bytes of the restored .wav file."""
         wave, peak = _lib.istft_ola_raw(mag, phase, self.frame_off, self.wave_off, self.n_songs,
                                         self.max_frames, self.total_wave)
-        if peak_normalize and self.total_wave > 0:
+        if pcm16:
+            if not peak_normalize:
+                raise _lib.SvsError("pcm16 output implies the 0.9 peak normalisation of data.py:162-166")
+            if self.total_wave > 0:
+                wave = _lib.wave_peak_normalize_pcm16_raw(wave, self.wave_off, peak, self.n_songs, 0.9)
+            else:
+                wave = wave.to(torch.int16)
+        elif peak_normalize and self.total_wave > 0:
             _lib.wave_peak_normalize_raw(wave, self.wave_off, peak, self.n_songs, 0.9)
         return wave, peak
 

@@ -64,20 +64,40 @@ class SpectrogramDataset:
         pad = INPUT_LEN - cur
         return torch.nn.functional.pad(mix, (0, pad)), torch.nn.functional.pad(voc, (0, pad))
 
-    def batches(self, batch_size, shuffle=True, rank=0, world=1):
+    def epoch_order(self, batch_size, shuffle=True, rank=0, world=1, epoch_seed=None):
+        """Item indices this rank visits in one epoch.  Single process: the reference's DataLoader order
+        (shuffle, last batch kept).  Data parallel: every rank shuffles with the SAME ``epoch_seed`` so that the
+        strided slices ``order[rank::world]`` partition the epoch, and the order is first padded (wrapping around,
+        like torch's DistributedSampler) to a multiple of ``world * batch_size`` so that all ranks run the same
+        number of full steps — a rank with an extra step would block forever in the gradient all-reduce."""
         order = list(range(len(self)))
         if shuffle:
-            self.rng.shuffle(order)
-        order = order[rank::world]
+            (random.Random(epoch_seed) if epoch_seed is not None else self.rng).shuffle(order)
+        if world > 1 and order:
+            per_step = world * batch_size
+            total = -(-len(order) // per_step) * per_step
+            while len(order) < total:
+                order += order[:total - len(order)]
+            order = order[rank::world]
+        return order
+
+    def batches(self, batch_size, shuffle=True, rank=0, world=1, epoch_seed=None):
+        order = self.epoch_order(batch_size, shuffle, rank, world, epoch_seed)
         for a in range(0, len(order), batch_size):
-            items = [self.item(i) for i in order[a:a + batch_size]]
-            mix = torch.stack([m for m, _ in items]).unsqueeze(1).contiguous()
-            voc = torch.stack([v for _, v in items]).unsqueeze(1).contiguous()
-            yield mix, voc
+            yield self.crop_batch(order[a:a + batch_size])
+
+    def crop_batch(self, indices):
+        """(mix, voc) float32 (B,1,512,128) for the given items (reference train.py:100-143 per item)."""
+        items = [self.item(i) for i in indices]
+        mix = torch.stack([m for m, _ in items]).unsqueeze(1).contiguous()
+        voc = torch.stack([v for _, v in items]).unsqueeze(1).contiguous()
+        return mix, voc
 
     def n_batches(self, batch_size, world=1):
-        per_rank = (len(self) + world - 1) // world
-        return (per_rank + batch_size - 1) // batch_size
+        if world > 1:
+            per_step = world * batch_size
+            return -(-len(self) // per_step)
+        return (len(self) + batch_size - 1) // batch_size
 
 
 def build_parser():
@@ -110,6 +130,10 @@ def validate(model, dataset, batch_size, rank=0, world=1):
         loss, _ = training.masked_l1(mask, mix, voc, two_term=True, want_grad=False)
         total += alpha_L1 * float(loss[0])
         n += 1
+    if world > 1:                                                    # every rank sees the same validation loss
+        acc = torch.tensor([total, float(n)], dtype=torch.float64, device=mix.device if n else "cuda")
+        torch.distributed.all_reduce(acc)
+        total, n = float(acc[0]), int(acc[1])
     return total / max(n, 1)
 
 
@@ -156,6 +180,10 @@ def main(argv=None):
         for t in list(model.parameters()) + list(model.buffers()):
             torch.distributed.broadcast(t.data, 0)
 
+    base_seed = torch.tensor([random.randrange(1 << 30)], dtype=torch.int64, device=device)
+    if world > 1:                                                    # one shuffle seed for all ranks (crop offsets
+        torch.distributed.broadcast(base_seed, 0)                    # keep their per-rank stream)
+    base_seed = int(base_seed)
     best_val, log_buffer = 100.0, []
     print(f"Start training for {args.epoch - start_epoch} epochs...")
     for ep in range(start_epoch, args.epoch):
@@ -167,9 +195,8 @@ def main(argv=None):
                 torch.save(make_checkpoint(model, ep + 1), f"CKPT/svs_{args.label}_400.pth")
             print(f"\n[Info] Epoch {ep}: Learning rate manually changed to 5e-4!\n")
         loss_sum, n_it = 0.0, 0
-        for mix, voc in train_set.batches(args.batch_size, shuffle=True, rank=rank, world=world):
-            if mix.shape[0] < 2:
-                continue                                             # batch-statistic BatchNorm needs > 1 sample
+        for mix, voc in train_set.batches(args.batch_size, shuffle=True, rank=rank, world=world,
+                                          epoch_seed=base_seed + ep if world > 1 else None):
             loss = training.train_step(model, mix, voc, two_term=True, loss_scale=alpha_L1)
             loss_sum += alpha_L1 * float(loss[0])                    # train.py:303 (.item() per step)
             n_it += 1
@@ -179,9 +206,10 @@ def main(argv=None):
             val = validate(model, valid_set, args.batch_size, rank, world)
             log_buffer.append(f"Val {val}\n")
             print(f"\n[Epoch {ep + 1}] Train Loss: {avg:.4e} | Val Loss: {val:.4e}")
-            if val < best_val and rank == 0:
+            if val < best_val:                                       # val is all-reduced: same decision on every rank
                 best_val = val
-                model.save(best_weight)                              # train.py:353-355
+                if rank == 0:
+                    model.save(best_weight)                          # train.py:353-355
             if rank == 0:
                 with open(log_file, "a") as f:
                     f.writelines(log_buffer)

@@ -128,6 +128,10 @@ def _raw_forward(model, mix, masks, update_running=True):
     ws = _workspace(model, b)
     arr = _layer_structs(model, None, masks, need_grads=False)
     mask = torch.empty_like(mix)
+    # the workspace holds everything the backward needs (saved activations, batch statistics, packed weights):
+    # stamp it so that a backward belonging to an EARLIER train-mode forward fails loudly instead of
+    # differentiating the wrong graph
+    model._train_gen = getattr(model, "_train_gen", 0) + 1
     with torch.cuda.device(mix.device):
         _lib.check(_lib.load().svs_unet_train_forward(arr, mix.data_ptr(), b, 1 if update_running else 0,
                                                       mask.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -154,12 +158,20 @@ class _TrainForward(torch.autograd.Function):
     def forward(ctx, mix, model, masks, *params):
         ctx.model, ctx.masks = model, masks
         ctx.save_for_backward(mix)
-        return _raw_forward(model, mix, masks)
+        mask = _raw_forward(model, mix, masks)
+        ctx.gen = model._train_gen
+        return mask
 
     @staticmethod
     def backward(ctx, grad_mask):
         (mix,) = ctx.saved_tensors
         model = ctx.model
+        if getattr(model, "_train_gen", 0) != ctx.gen:
+            raise _lib.SvsError(
+                "UNet backward: another train-mode forward ran on this model after the forward being "
+                "differentiated.  The saved activations live in ONE per-model workspace (not in the autograd "
+                "graph), so only the most recent train-mode forward can be back-propagated: call backward() "
+                "before the next forward (for gradient accumulation sum the .grad tensors, not the losses).")
         grads = [torch.empty_like(p) for p in param_list(model)]
         _raw_backward(model, mix, grad_mask.contiguous().float(), ctx.masks, grads)
         return (None, None, None) + tuple(grads)
@@ -179,17 +191,22 @@ def train_forward(model, mix, injected_masks=None):
 def masked_l1(mask, mix, voc, two_term=True, grad_scale=1.0, want_grad=True):
     """svs_l1_masked_loss: (loss tensor [3] = total / vocal / accompaniment, dL/dmask or None)."""
     loss = torch.empty(3, dtype=torch.float32, device=mask.device)
+    scratch = torch.empty(_lib.L1_SCRATCH_FLOATS, dtype=torch.float32, device=mask.device)   # per call: stream safe
     grad = torch.empty_like(mask) if want_grad else None
     with torch.cuda.device(mask.device):
         _lib.check(_lib.load().svs_l1_masked_loss(mask.data_ptr(), mix.data_ptr(), voc.data_ptr(), mask.numel(),
                                                   1 if two_term else 0, float(grad_scale), loss.data_ptr(),
                                                   grad.data_ptr() if grad is not None else None,
-                                                  _lib.stream_ptr(mask.device)), "svs_l1_masked_loss")
+                                                  scratch.data_ptr(), _lib.stream_ptr(mask.device)),
+                   "svs_l1_masked_loss")
     return loss, grad
 
 
+TRAIN_PRECISION = "fp32"
+
+
 def train_step(model, mix, voc, two_term: bool = True, loss_scale: float = 1.0, step: bool = True,
-               injected_masks=None):
+               injected_masks=None, sync_grads: bool = True):
     """One fused optimisation step (reference train.py:271-300 without the MR-STFT term).
 
     Returns the device tensor [total, vocal, accompaniment] of the UNSCALED L1 loss.  Gradients are
@@ -207,7 +224,7 @@ def train_step(model, mix, voc, two_term: bool = True, loss_scale: float = 1.0, 
         _raw_backward(model, mix, grad_mask, masks, views)
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
-            if world > 1:
+            if world > 1 and sync_grads:
                 torch.distributed.all_reduce(flat)
                 flat.div_(world)
         for p, g in zip(param_list(model), views):

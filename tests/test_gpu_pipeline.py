@@ -123,3 +123,86 @@ def test_host_streamer_matches_direct_forward():
     for a, b in zip(hin, hout):
         ref = net.separate(a.cuda(), vocal_solo=True).cpu()
         assert torch.equal(b, ref)
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 1e-2), ("tf32", 1e-3)])
+def test_three_minute_round_trip_matches_oracle(precision, tol):
+    # BASELINE configs[2]: one synthetic 180 s mixture (1,474,560 samples, 1,921 frames, 16 patches) through the
+    # production Separator (512-patch UNet batches, staged patches) against to_spec -> inference loop -> to_wave
+    mix, voc, _ = synth.synth_song(180.0, seed=1234)
+    torch.manual_seed(0)
+    net = svs_model.UNet(precision=precision).eval().cuda()
+    sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    sep = pipeline.Separator(net, max_batch=512)
+    batch = spectral.SongBatch.from_audio([mix])
+    wave, peak, mag, phase, out_mag = sep.separate_batch(batch, vocal_solo=True, return_spec=True)
+    spec_ref, pred_ref, y_ref = _oracle_song(sd, mix, True)
+    got_spec = batch.song_spec(mag, 0).cpu().numpy()
+    assert got_spec.shape == spec_ref.shape == (513, 1921)
+    assert np.abs(got_spec - spec_ref).max() <= 1e-4                  # normalised: max == 1
+    got = batch.song_spec(out_mag, 0).cpu().numpy()
+    assert np.abs(got - pred_ref).max() <= tol
+    y = batch.song_wave(wave, 0).cpu().numpy()
+    assert y.shape == y_ref.shape == (1474560,)
+    d = abs(synth.sdr_db(voc, y) - synth.sdr_db(voc, y_ref))
+    assert d <= 0.05, d                                               # north_star: within 0.05 dB SDR
+    assert synth.sdr_db(y_ref, y) > (30.0 if precision == "bf16" else 50.0)
+
+
+def test_rank_shard_of_the_corpus_matches_per_song_and_oracle():
+    # the N = 8 geometry of BASELINE configs[3]: 19 three-minute songs = 304 patches in ONE ragged 512-slot batch;
+    # every song must come out as it does alone, and two of them are checked against the oracle
+    songs = [synth.synth_song(180.0, seed=1234 + 8 * i) for i in range(19)]
+    torch.manual_seed(0)
+    net = svs_model.UNet(precision="bf16").eval().cuda()
+    sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    sep = pipeline.Separator(net, max_batch=512)
+    waves = sep.separate([s[0] for s in songs])
+    assert len(waves) == 19 and all(len(w) == 1474560 for w in waves)
+    for i in (0, 7, 18):
+        alone = sep.separate([songs[i][0]])[0]
+        # same kernels; tile / split-K choices depend on the UNet batch (304 vs 16 patches)
+        assert np.abs(alone - waves[i]).max() <= 2e-3
+    for i in (3, 18):
+        mix, voc, _ = songs[i]
+        _, _, y_ref = _oracle_song(sd, mix, True)
+        assert abs(synth.sdr_db(voc, waves[i]) - synth.sdr_db(voc, y_ref)) <= 0.05
+
+
+def test_song_streamer_overlapping_unet_sections_do_not_share_a_workspace():
+    # several equal-size multi-patch chunks on four streams with a SLOW UNet (fp32 CUDA-core mode) so that the
+    # UNet sections of different streams certainly overlap: each stream must own its activation workspace
+    songs = [synth.synth_song(25.0, seed=40 + i)[0] for i in range(8)]          # 3 patches each
+    torch.manual_seed(0)
+    net = svs_model.UNet(precision="fp32").eval().cuda()
+    ref = pipeline.Separator(net, max_batch=6).separate(songs)
+    lengths = [len(s) for s in songs]
+    host_in = torch.from_numpy(np.concatenate(songs).astype(np.float32)).pin_memory()
+    host_out = torch.empty(sum(768 * (n // 768) for n in lengths), dtype=torch.float32).pin_memory()
+    st = pipeline.SongStreamer(net, songs_per_chunk=2, n_streams=4)
+    for _ in range(2):
+        wl = st.run(host_in, lengths, host_out)
+        torch.cuda.synchronize()
+        off = 0
+        for r, n in zip(ref, wl):
+            assert np.abs(host_out[off:off + n].numpy() - r).max() <= 1e-5
+            off += n
+
+
+def test_song_streamer_pcm16_in_and_out():
+    songs = [synth.synth_song(14.0 + i, seed=60 + i)[0] for i in range(4)]
+    pcm = [np.clip(np.rint(s * 32768.0), -32768, 32767).astype(np.int16) for s in songs]    # what a PCM_16 .wav holds
+    torch.manual_seed(0)
+    net = svs_model.UNet(precision="bf16").eval().cuda()
+    ref = pipeline.Separator(net).separate([p.astype(np.float32) / 32768.0 for p in pcm])  # float path, same samples
+    lengths = [len(s) for s in songs]
+    host_in = torch.from_numpy(np.concatenate(pcm)).pin_memory()
+    host_out = torch.empty(sum(768 * (n // 768) for n in lengths), dtype=torch.int16).pin_memory()
+    wl = pipeline.SongStreamer(net, songs_per_chunk=2).run(host_in, lengths, host_out)
+    torch.cuda.synchronize()
+    off = 0
+    for r, n in zip(ref, wl):
+        want = np.rint(r.astype(np.float64) * 32767.0)
+        got = host_out[off:off + n].numpy().astype(np.float64)
+        assert np.abs(got - want).max() <= 2e-3 * 32767                # split-K / batch-size dependent last bits
+        off += n

@@ -103,3 +103,38 @@ def test_istft_is_bit_reproducible():
     for i, y in enumerate(songs):
         got = batch.song_wave(w1, i).cpu().numpy()
         assert np.abs(got - y).max() < 1e-5
+
+
+def test_cuda_stft_matches_analytic_known_answers():
+    # library-independent vectors (tests/test_oracle_spectral.py): bin-centred sinusoids and an impulse
+    from test_oracle_spectral import impulse_kat, sinusoid_kat
+    for k0 in (2, 37, 256, 510):
+        y, t, expect = sinusoid_kat(k0)
+        d = spectral.stft(y)
+        assert np.abs(d[:, t] - expect).max() <= 1e-4 * 256.0, k0    # north_star: 1e-4 of the spectrum max
+    y, expect = impulse_kat()
+    d = spectral.stft(y)
+    assert np.abs(d - expect).max() <= 1e-4
+    yr = spectral.istft(d.astype(np.complex64))
+    assert np.abs(yr - y).max() < 1e-5
+
+
+def test_pcm16_boundary_matches_the_float_path():
+    # reference data.py:78 (librosa.load of a PCM_16 file = int16 / 32768) and data.py:166 (sf.write PCM_16 =
+    # lrintf(y * 0x7FFF)): the int16 entry points must equal "convert on the host, then the float kernels"
+    rng = np.random.default_rng(5)
+    songs16 = [rng.integers(-20000, 20000, size=n, dtype=np.int16) for n in (768 * 9 + 3, 5000, 768 * 40)]
+    songs32 = [s.astype(np.float32) / 32768.0 for s in songs16]
+    b32 = spectral.SongBatch.from_audio(songs32)
+    pcm = torch.from_numpy(np.concatenate(songs16)).cuda()
+    b16 = spectral.SongBatch(pcm, [len(s) for s in songs16])
+    m32, p32, x32 = b32.stft()
+    m16, p16, x16 = b16.stft()
+    assert torch.equal(m32, m16) and torch.equal(p32, p16) and torch.equal(x32, x16)    # same arithmetic after the load
+    wave, peak = b32.istft(m32, p32, peak_normalize=False)
+    q, _ = b32.istft(m32, p32, peak_normalize=True, pcm16=True)
+    assert q.dtype == torch.int16 and q.shape == wave.shape
+    norm, _ = b32.istft(m32, p32, peak_normalize=True)
+    ref = np.clip(np.rint(norm.cpu().numpy().astype(np.float64) * 32767.0), -32768, 32767)
+    assert np.abs(q.cpu().numpy().astype(np.int64) - ref.astype(np.int64)).max() <= 1   # fp32 vs fp64 product at ties
+    assert int(q.abs().max()) == int(round(0.9 * 32767))

@@ -64,7 +64,7 @@ def test_grads_match_oracle_elementwise_with_dropout_masks():
     assert abs(float(loss[0]) - float(ref_loss.detach())) <= 1e-4 * float(ref_loss.detach())
     assert abs(float(loss[0]) - float(loss[1]) - float(loss[2])) < 1e-6
     for name, p in net.named_parameters():
-        ref = params[name].grad
+        ref = params[name].grad.float()
         got = p.grad.cpu()
         denom = max(float(ref.norm()), 1e-6)
         assert float((got - ref).norm()) / denom <= 1e-3 or float((got - ref).abs().max()) < 1e-7, name
@@ -93,3 +93,57 @@ def test_fused_loss_kernel_matches_torch():
         loss, grad = training.masked_l1(m.detach(), mix, voc, two_term=two)
         assert abs(float(loss[0]) - float(ref)) < 1e-6
         assert torch.allclose(grad, gref, atol=1e-9)
+
+
+def _oracle_step(net, mix, voc, masks=None, dtype=torch.float32):
+    """Oracle autograd step.  dtype=float64 makes the tolerance measure OUR error only: at batch 64 a weight
+    gradient is a sum over up to a million pixels with heavy cancellation, and the fp32 summation order of the CPU
+    oracle itself is then worth ~1e-3 of the result."""
+    sd = {k: (v.detach().cpu().to(dtype) if v.is_floating_point() else v.detach().cpu().clone())
+          for k, v in net.state_dict().items()}
+    params = {k: v.requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    ref_mask = unet_oracle.unet_forward(params, mix.to(dtype), training=True, dropout_masks=masks)
+    ref_loss = unet_oracle.l1_masked_loss(ref_mask, mix.to(dtype), voc.to(dtype), two_term=True)
+    ref_loss.backward()
+    return float(ref_loss.detach()), params
+
+
+def _check_grads(net, params, rel=1e-3):
+    for name, p in net.named_parameters():
+        ref = params[name].grad.float()
+        got = p.grad.cpu()
+        denom = max(float(ref.norm()), 1e-6)
+        assert float((got - ref).norm()) / denom <= rel or float((got - ref).abs().max()) < 1e-7, \
+            (name, float((got - ref).norm()) / denom)
+
+
+def test_train_step_at_the_benched_batch_64_matches_oracle_autograd():
+    # BASELINE configs[4] / SURVEY 8(d) config 5: batch 64 per GPU, mix = rand, voc = mix * rand, dropout masks
+    # injected (torch's Philox stream cannot be matched), BatchNorm in train mode
+    net = _net(0.5)
+    mix, voc = _data(seed=0, n=64)
+    g = torch.Generator().manual_seed(9)
+    masks = {f"deconv{i}": torch.rand(64, c, generator=g) >= 0.5 for i, c in zip(range(1, 6), [256, 128, 64, 32, 16])}
+    ref_loss, params = _oracle_step(net, mix, voc, masks, dtype=torch.float64)
+    loss = training.train_step(net, mix.cuda(), voc.cuda(), two_term=True, step=False, injected_masks=masks)
+    assert abs(float(loss[0]) - ref_loss) <= 1e-4 * ref_loss          # loss rel 1e-4
+    _check_grads(net, params, rel=1e-3)                               # grad rel-L2 1e-3 (TF32 bound of SURVEY 8d)
+
+
+def test_train_step_batch_one_matches_oracle():
+    # torch BatchNorm trains with B = 1 whenever H*W > 1 (every layer here has >= 16 pixels per channel)
+    net = _net(0.0)
+    mix, voc = _data(seed=4, n=1)
+    ref_loss, params = _oracle_step(net, mix, voc)
+    loss = training.train_step(net, mix.cuda(), voc.cuda(), two_term=True, step=False)
+    assert abs(float(loss[0]) - ref_loss) <= 1e-4 * ref_loss
+    _check_grads(net, params, rel=1e-3)
+
+
+def test_stale_backward_raises():
+    net = _net(0.0)
+    mix, voc = _data(seed=6, n=2)
+    m1 = net(mix.cuda())
+    _ = net(mix.cuda())                                               # a second train-mode forward overwrites the workspace
+    with pytest.raises(RuntimeError, match="most recent train-mode forward"):
+        m1.sum().backward()

@@ -100,3 +100,57 @@ def test_checkpoint_round_trip(tmp_path):
     x = _x(11, 1).cuda()
     with torch.no_grad():
         assert torch.equal(net(x), net2(x))
+
+
+def _oracle_chunked(sd, x, chunk=64):
+    out = []
+    with torch.no_grad():
+        for a in range(0, x.shape[0], chunk):
+            out.append(unet_oracle.unet_forward(sd, x[a:a + chunk]))
+    return torch.cat(out)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_mask_matches_oracle_at_the_benched_batch_64_under_a_cuda_graph(precision):
+    # BASELINE configs[1] exactly as bench.py times it: batch 64, torch.rand patches, CUDA-graph replay
+    net = _net(bn_seed=6)
+    x = _x(64, 64)
+    ref = _oracle_chunked(net.state_dict(), x)
+    net = net.cuda()
+    net.precision = precision
+    plan = net.plan()
+    xd, yd = x.cuda(), torch.empty(64, 1, 512, 128, device="cuda")
+    plan.forward_dense(xd, 0, yd)                                     # warm-up (allocates the workspace)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            plan.forward_dense(xd, 0, yd)
+    torch.cuda.current_stream().wait_stream(side)
+    yd.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    err = (yd.cpu() - ref).abs().max().item()
+    assert err <= TOL[precision], err
+    g.replay()                                                        # replays are bit-identical
+    torch.cuda.synchronize()
+    first = yd.clone()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(first, yd)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_mask_matches_oracle_at_the_pipeline_batch_512(precision):
+    # pipeline.Separator's UNet batch (max_batch = 512): 296-/148-CTA grids, wide tiles, no split-K
+    net = _net(bn_seed=8)
+    x = _x(512, 512)
+    ref = _oracle_chunked(net.state_dict(), x)
+    net = net.cuda()
+    net.precision = precision
+    with torch.no_grad():
+        mask = net(x.cuda())
+    err = (mask.cpu() - ref).abs().max().item()
+    assert err <= TOL[precision], err

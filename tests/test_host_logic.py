@@ -102,3 +102,25 @@ def test_gloo_world_size_2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_data_parallel_epoch_order_is_a_partition_with_equal_steps():
+    # train.SpectrogramDataset.epoch_order: every rank shuffles with the shared epoch seed, the order is padded to
+    # a multiple of world * batch so that all ranks run the same number of full steps (else the all-reduce hangs)
+    import random
+    from svs_unet_pytorch_b200 import train as svs_train
+    ds = svs_train.SpectrogramDataset.__new__(svs_train.SpectrogramDataset)
+    ds.file_names = [f"{i:04d}" for i in range(7)]
+    ds.samples_per_song = 9                                         # 63 items
+    for world in (2, 3, 5, 8):
+        for bs in (2, 4):
+            ds.rng = random.Random(1)
+            orders = [ds.epoch_order(bs, True, r, world, epoch_seed=77) for r in range(world)]
+            assert len({len(o) for o in orders}) == 1 and len(orders[0]) % bs == 0
+            assert len(orders[0]) // bs == ds.n_batches(bs, world)
+            seen = sum(orders, [])
+            assert set(seen) == set(range(63))                      # nobody is skipped
+            assert len(seen) - 63 < world * bs                      # only the wrap-around padding repeats
+    ds.rng = random.Random(1)
+    single = ds.epoch_order(4, True, 0, 1)
+    assert sorted(single) == list(range(63)) and ds.n_batches(4, 1) == 16   # reference DataLoader: last batch kept

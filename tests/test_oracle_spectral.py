@@ -71,3 +71,54 @@ def test_to_wave_peak_normalises():
     y = so.to_wave(spec, ph)
     assert abs(np.abs(y).max() - 0.9) < 1e-6
     assert synth.sdr_db(mix[: len(y)], y) > 60.0
+
+
+# ---------------------------------------------------------------------------------------------
+# Analytic known-answer vectors: a third, library-independent check of the restatement (the librosa boundary
+# itself stays UNPINNED: librosa is absent here and the reference ships no vectors).
+# Periodic Hann has the 3-term spectrum W[0] = N/2, W[+-1] = -N/4, so for x[n] = cos(2 pi k0 n / N):
+#   X_t[k0] = N/4 * exp(2 pi i k0 s_t / N),  X_t[k0 +- 1] = -N/8 * (same phasor),  all other bins 0,
+# for every frame whose window lies inside the signal; s_t = 768 t - 512 is the frame's first sample.
+
+def sinusoid_kat(k0: int, n_frames: int = 12):
+    n = 768 * (n_frames - 1)
+    y = np.cos(2 * np.pi * k0 * np.arange(n) / 1024.0).astype(np.float32)
+    t = np.arange(1, n_frames - 1)                                    # interior frames (no centre padding)
+    phasor = np.exp(2j * np.pi * k0 * (768 * t - 512) / 1024.0)
+    expect = np.zeros((513, len(t)), dtype=np.complex128)
+    expect[k0] = 256.0 * phasor
+    expect[k0 - 1] = -128.0 * phasor
+    expect[k0 + 1] = -128.0 * phasor
+    return y, t, expect
+
+
+def impulse_kat(n0: int = 3000, n_frames: int = 8):
+    n = 768 * (n_frames - 1)
+    y = np.zeros(n, dtype=np.float32)
+    y[n0] = 1.0
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(1024) / 1024.0)
+    expect = np.zeros((513, n_frames), dtype=np.complex128)
+    k = np.arange(513)
+    for t in range(n_frames):
+        m = n0 - (768 * t - 512)                                      # position of the impulse inside frame t
+        if 0 <= m < 1024:
+            expect[:, t] = w[m] * np.exp(-2j * np.pi * k * m / 1024.0)
+    return y, expect
+
+
+def test_stft_bin_centred_sinusoids_known_answer():
+    for k0 in (2, 37, 256, 510):
+        y, t, expect = sinusoid_kat(k0)
+        d = so.stft(y)[:, t]
+        assert np.abs(d - expect).max() <= 2e-5 * 256.0, k0          # float32 input quantisation only
+        mag, ph = so.magphase(so.stft(y))
+        assert np.abs(mag[k0, t] - 256.0).max() < 1e-2 and np.abs(mag[k0 + 1, t] - 128.0).max() < 1e-2
+        assert np.abs(ph[k0, t] - expect[k0] / 256.0).max() < 1e-4
+
+
+def test_stft_impulse_known_answer_and_round_trip():
+    y, expect = impulse_kat()
+    d = so.stft(y)
+    assert np.abs(d - expect).max() <= 1e-6
+    yr = so.istft(d)
+    assert np.abs(yr - y).max() < 1e-6                                # sum_t w^2 / envelope == 1 exactly where covered
