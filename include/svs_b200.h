@@ -218,17 +218,41 @@ typedef struct svs_train_layer {
                                                   deconv1..deconv5 (reference model.py:80-108)            */
 } svs_train_layer;
 
+/* Arithmetic of the step.  A train plan selects TF32 on the tensor cores (tcgen05 kind::tf32, fp32 accumulate) for the
+ * forward, data-gradient and weight-gradient convolutions — what torch + cuDNN do by default for the reference's
+ * fp32 model on a GPU (torch.backends.cudnn.allow_tf32) — while BatchNorm statistics, normalisation, the loss and every
+ * reduction stay fp32.  plan == NULL runs the whole step in exact fp32 on CUDA cores (parity mode).  The plan owns
+ * only device scratch for repacked weights (rewritten by every forward call); it holds no parameters and may be
+ * shared by successive steps, not by concurrent ones. */
+typedef struct svs_train_plan svs_train_plan;
+int svs_unet_train_plan_create(void* stream, svs_train_plan** plan_out);
+int svs_unet_train_plan_destroy(svs_train_plan* plan);
+
 size_t svs_unet_train_workspace_bytes(int batch);
 
-/* mix float32 dense (batch,1,512,128) -> mask float32 dense (batch,1,512,128).  The workspace keeps
- * everything the backward needs and must stay untouched until svs_unet_train_backward returns. */
-int svs_unet_train_forward(const svs_train_layer layers[12], const float* mix, int batch,
+/* mix float32 dense (batch,1,512,128) -> mask float32 dense (batch,1,512,128).  The workspace (1024-byte aligned)
+ * keeps everything the backward needs and must stay untouched until svs_unet_train_backward returns. */
+int svs_unet_train_forward(const svs_train_plan* plan, const svs_train_layer layers[12], const float* mix, int batch,
                            int update_running_stats, float* mask_out, void* workspace, size_t workspace_bytes,
                            void* stream);
 
-/* grad_mask = dLoss/dmask (dense, same shape as the mask).  Fills grad_* of all 12 layers. */
-int svs_unet_train_backward(const svs_train_layer layers[12], const float* mix, const float* grad_mask,
-                            int batch, void* workspace, size_t workspace_bytes, void* stream);
+/* grad_mask = dLoss/dmask (dense, same shape as the mask).  Fills grad_* of all 12 layers.  `plan` must be the one
+ * (or NULL) the forward ran with. */
+int svs_unet_train_backward(const svs_train_plan* plan, const svs_train_layer layers[12], const float* mix,
+                            const float* grad_mask, int batch, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The weight-gradient contraction on its own (the wgrad half of loss.backward() through nn.Conv2d /
+ * nn.ConvTranspose2d, reference model.py:47-109), TF32 on tcgen05:
+ *     grad_w[(m * l_c + n) * 25 + kh * 5 + kw] = sum_{b,y,x} S[b,y,x,s_coff+m] * L[b, 2y+kh-2, 2x+kw-2, l_coff+n]
+ * S: fp32 NHWC [batch][gh][gw][s_pitch] (small grid; Conv2d: dL/dout, ConvTranspose2d: the layer input),
+ * L: fp32 NHWC [batch][2gh][2gw][l_pitch] (Conv2d: the layer input, ConvTranspose2d: dL/dout); out-of-range taps
+ * read zero.  Result in the torch layout (s_c, l_c, 5, 5).  Requirements: s_c % 32 == 0, l_c % 16 == 0, pitches and
+ * offsets % 4 == 0, power-of-two grids; values should be TF32-representable (the tensor core truncates).
+ * `partial`: device scratch of svs_conv_wgrad_partial_floats() floats (fixed-order split reduction). */
+size_t svs_conv_wgrad_partial_floats(int gh, int gw, int batch, int s_c, int l_c);
+int svs_conv_wgrad_tf32(const float* small, int s_pitch, int s_coff, int s_c, const float* large, int l_pitch,
+                        int l_coff, int l_c, int gh, int gw, int batch, float* partial, size_t partial_floats,
+                        float* grad_w, void* stream);
 
 /* Fused loss of reference train.py:275-283 and its gradient w.r.t. the mask:
  *   L = mean|m*x - v| (+ mean|(1-m)*x - max(x - v, 0)| when two_term)      n = number of elements

@@ -73,11 +73,16 @@ _SIGNATURES = [
     ("svs_debug_set_trace", c_int, [c_void_p, c_int]),
     ("svs_unet_read_activation", c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     ("svs_unet_launch_count", c_int, [c_void_p, c_int]),
+    ("svs_unet_train_plan_create", c_int, [c_void_p, POINTER(c_void_p)]),
+    ("svs_unet_train_plan_destroy", c_int, [c_void_p]),
     ("svs_unet_train_workspace_bytes", c_size_t, [c_int]),
-    ("svs_unet_train_forward", c_int, [POINTER(TrainLayer), c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
-                                       c_void_p]),
-    ("svs_unet_train_backward", c_int, [POINTER(TrainLayer), c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+    ("svs_unet_train_forward", c_int, [c_void_p, POINTER(TrainLayer), c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]),
+    ("svs_unet_train_backward", c_int, [c_void_p, POINTER(TrainLayer), c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                         c_void_p]),
+    ("svs_conv_wgrad_partial_floats", c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    ("svs_conv_wgrad_tf32", c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_size_t, c_void_p, c_void_p]),
     ("svs_l1_masked_loss", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
 ]
@@ -250,6 +255,48 @@ def patches_scatter_raw(patches, patch_off, in_frames, spec, dc_zero=True):
                                          in_frames.data_ptr() if in_frames is not None else None, spec.data_ptr(), n,
                                          1 if dc_zero else 0, stream_ptr(spec.device)), "svs_patches_scatter")
     return spec
+
+
+def conv_wgrad_tf32(small: torch.Tensor, large: torch.Tensor, s_coff: int = 0, s_c: int | None = None,
+                    l_coff: int = 0, l_c: int | None = None) -> torch.Tensor:
+    """Weight gradient of a 5x5 stride-2 Conv2d / ConvTranspose2d on tcgen05 (svs_conv_wgrad_tf32): ``small`` fp32 NHWC
+    (B, gh, gw, Cs), ``large`` fp32 NHWC (B, 2gh, 2gw, Cl) -> (s_c, l_c, 5, 5)."""
+    require_cuda(small, "small", torch.float32)
+    require_cuda(large, "large", torch.float32)
+    check_device(small.device)
+    b, gh, gw, sp = small.shape
+    lp = large.shape[3]
+    s_c = sp - s_coff if s_c is None else s_c
+    l_c = lp - l_coff if l_c is None else l_c
+    n = load().svs_conv_wgrad_partial_floats(gh, gw, b, s_c, l_c)
+    partial = torch.empty(n, dtype=torch.float32, device=small.device)
+    out = torch.empty((s_c, l_c, 5, 5), dtype=torch.float32, device=small.device)
+    with torch.cuda.device(small.device):
+        check(load().svs_conv_wgrad_tf32(small.data_ptr(), sp, s_coff, s_c, large.data_ptr(), lp, l_coff, l_c, gh, gw, b,
+                                         partial.data_ptr(), n, out.data_ptr(), stream_ptr(small.device)),
+              "svs_conv_wgrad_tf32")
+    return out
+
+
+class TrainPlan:
+    """svs_train_plan: TF32 tensor-core arithmetic for the training step (device scratch for repacked weights)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        check_device(self.device)
+        handle = c_void_p()
+        with torch.cuda.device(self.device):
+            check(load().svs_unet_train_plan_create(stream_ptr(self.device), byref(handle)), "svs_unet_train_plan_create")
+            torch.cuda.current_stream(self.device).synchronize()
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().svs_unet_train_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------

@@ -234,8 +234,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               f[i + 3] = tc_act(__uint_as_float(v[h + i + 3]) + bv.w, p.act);
             }
             if constexpr (kTf32) {
+              if ((p.out_flags & OUT_ACCUMULATE) && valid) {          // data gradients meeting at a skip connection
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = round_tf32(f[i]);
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dst) + i);
+                  f[i] += o.x; f[i + 1] += o.y; f[i + 2] += o.z; f[i + 3] += o.w;
+                }
+              }
+              if (!(p.out_flags & OUT_KEEP_FP32)) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = round_tf32(f[i]);
+              }
             }
             if (valid) store16(dst, f);
           }
@@ -312,7 +321,13 @@ splitk_finish_kernel(const TcParams p) {
     u.y = *reinterpret_cast<uint32_t*>(&c);
     *reinterpret_cast<uint2*>(dst) = u;
   } else {
-    *reinterpret_cast<float4*>(dst) = make_float4(round_tf32(o[0]), round_tf32(o[1]), round_tf32(o[2]), round_tf32(o[3]));
+    float4 r = make_float4(o[0], o[1], o[2], o[3]);
+    if (p.out_flags & OUT_ACCUMULATE) {
+      const float4 old = *reinterpret_cast<const float4*>(dst);
+      r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+    }
+    if (!(p.out_flags & OUT_KEEP_FP32)) r = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
+    *reinterpret_cast<float4*>(dst) = r;
   }
 }
 
@@ -379,9 +394,11 @@ int encode_tensor_map(CUtensorMap* map, bool tf32, int rank, void* base, const c
   PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
   if (!fn) return fail(SVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // swz 12832 = 128-byte span swizzled in 32-byte atoms (the only layout tcgen05 accepts for MN-major TF32 operands)
   const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                : swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+                                : swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : swz == 12832 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base,
                   dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -389,9 +406,9 @@ int encode_tensor_map(CUtensorMap* map, bool tf32, int rank, void* base, const c
   return SVS_OK;
 }
 
-static int make_tmap_a(const TcLayer& t, const LayerGeom& g, void* buf, int batch, int es, bool tf32,
-                       CUtensorMap* out) {
-  const cuuint64_t ct = kBufGeom[g.in_buf].c;
+static int make_tmap_a(const TcLayer& t, const void* buf, int batch, int es, bool tf32, CUtensorMap* out) {
+  const ConvDesc& g = t.d;
+  const cuuint64_t ct = g.in_pitch;
   const cuuint64_t H = g.hin, W = g.win;
   cuuint64_t dims[5], strides[4];
   if (!g.transposed) {
@@ -403,7 +420,7 @@ static int make_tmap_a(const TcLayer& t, const LayerGeom& g, void* buf, int batc
   }
   const cuuint32_t box[5] = {static_cast<cuuint32_t>(t.block_k), static_cast<cuuint32_t>(t.bw), 1,
                              static_cast<cuuint32_t>(t.bh), static_cast<cuuint32_t>(t.nb)};
-  return encode_tensor_map(out, tf32, 5, buf, dims, strides, box, t.swz);
+  return encode_tensor_map(out, tf32, 5, const_cast<void*>(buf), dims, strides, box, t.swz);
 }
 
 static unsigned tc_disable_mask() {
@@ -411,139 +428,167 @@ static unsigned tc_disable_mask() {
   return e ? static_cast<unsigned>(std::strtoul(e, nullptr, 0)) : 0u;
 }
 
+// (Re)packs the weights of a planned problem from w_fold [25][cin][cout] fp32 (stream ordered; the training step
+// calls this every iteration, the inference plan once).
+int tc_pack_one(TcLayer& t, const float* w_fold, bool tf32, cudaStream_t st) {
+  const ConvDesc& g = t.d;
+  const int n_total = t.merged ? 4 * g.cout : g.cout;
+  for (int ph = 0; ph < t.n_phases; ++ph) {
+    const TcPhase& phs = t.phases[ph];
+    const size_t n = static_cast<size_t>(n_total) * t.k_total[ph];
+    const size_t off = static_cast<size_t>(phs.b_elem_off);
+    const unsigned blocks = static_cast<unsigned>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
+    if (t.merged && tf32)
+      tc_pack_weights_merged_kernel<float><<<blocks, 256, 0, st>>>(w_fold, g.cin, g.cout, t.d_src, phs.n_chunks,
+                                                                  t.block_k, static_cast<float*>(t.d_weights));
+    else if (t.merged)
+      tc_pack_weights_merged_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+          w_fold, g.cin, g.cout, t.d_src, phs.n_chunks, t.block_k, static_cast<__nv_bfloat16*>(t.d_weights));
+    else if (tf32)
+      tc_pack_weights_kernel<float><<<blocks, 256, 0, st>>>(w_fold, g.cin, g.cout, t.d_src + phs.chunk_begin,
+                                                           phs.n_chunks, t.block_k,
+                                                           static_cast<float*>(t.d_weights) + off);
+    else
+      tc_pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+          w_fold, g.cin, g.cout, t.d_src + phs.chunk_begin, phs.n_chunks, t.block_k,
+          static_cast<__nv_bfloat16*>(t.d_weights) + off);
+    SVS_CHECK_LAUNCH("tc_pack_weights_kernel");
+  }
+  return SVS_OK;
+}
+
+// Plans one problem: tiling, K-chunk schedule, device tables, weight buffer + tensor maps.  `w_fold` may be null
+// (weights are packed later with tc_pack_one).  Leaves t.enabled == false when the shape has no tcgen05 mapping.
+int tc_plan_one(TcLayer& t, const ConvDesc& g, const float* w_fold, bool tf32, cudaStream_t st) {
+  const int es = tf32 ? 4 : 2;
+  t.d = g;
+  t.enabled = false;
+  int swz = g.cin * es >= 128 ? 128 : g.cin * es;     // one swizzle row = min(128 B, all input channels)
+  if (swz != 32 && swz != 64 && swz != 128) return SVS_OK;
+  t.swz = swz;
+  t.block_k = swz / es;
+  const char* no_merge = std::getenv("SVS_TC_NO_MERGE");
+  t.merged = g.transposed && 4 * g.cout <= 256 && !(no_merge && no_merge[0] == '1');
+  const int n_total = t.merged ? 4 * g.cout : g.cout;
+  t.block_n = n_total < 256 ? (n_total < 128 ? n_total : 128) : (t.merged ? 256 : 128);
+  if (n_total % t.block_n != 0 || (t.block_n != 16 && t.block_n != 32 && t.block_n != 64 && t.block_n != 128 &&
+                                   t.block_n != 256))
+    return SVS_OK;
+  t.gw = g.transposed ? g.win : g.wout;
+  t.gh = g.transposed ? g.hin : g.hout;
+  t.bw = t.gw < 16 ? t.gw : 16;
+  t.bh = t.gh < 128 / t.bw ? t.gh : 128 / t.bw;
+  t.nb = 128 / (t.bw * t.bh);
+  // ---- K-chunk schedule ----
+  std::vector<int2> src;
+  const int ct = g.in_pitch;
+  t.chunks.clear();
+  if (!g.transposed) {
+    t.n_phases = 1;
+    t.phases[0] = TcPhase{0, 0, 0, 0, 0};
+    for (int kh = 0; kh < 5; ++kh)
+      for (int kw = 0; kw < 5; ++kw) {
+        const int qh = kh - 2, qw = kw - 2;
+        const int ph = qh & 1, pw = qw & 1;
+        const int dh = (qh - ph) / 2, dw = (qw - pw) / 2;
+        for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
+          t.chunks.push_back(TcChunk{pw * ct + g.in_coff + c0, dw, ph, dh});
+          src.push_back(make_int2(kh * 5 + kw, c0));
+        }
+      }
+    t.phases[0].n_chunks = static_cast<int>(t.chunks.size());
+  } else if (t.merged) {
+    t.n_phases = 1;
+    t.phases[0] = TcPhase{0, 0, 0, 0, 0};
+    for (int dh = 1; dh >= -1; --dh)
+      for (int dw = 1; dw >= -1; --dw)
+        for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
+          t.chunks.push_back(TcChunk{g.in_coff + c0, dw, 0, dh});
+          src.push_back(make_int2((dh + 1) * 3 + (dw + 1), c0));
+        }
+    t.phases[0].n_chunks = static_cast<int>(t.chunks.size());
+  } else {
+    t.n_phases = 4;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        TcPhase& phs = t.phases[py * 2 + px];
+        phs.py = py; phs.px = px;
+        phs.chunk_begin = static_cast<int>(t.chunks.size());
+        for (int kh = py; kh < 5; kh += 2)
+          for (int kw = px; kw < 5; kw += 2) {
+            const int dh = (py + 2 - kh) / 2, dw = (px + 2 - kw) / 2;
+            for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
+              t.chunks.push_back(TcChunk{g.in_coff + c0, dw, 0, dh});
+              src.push_back(make_int2(kh * 5 + kw, c0));
+            }
+          }
+        phs.n_chunks = static_cast<int>(t.chunks.size()) - phs.chunk_begin;
+      }
+  }
+  // ---- upload schedule, weight buffer, B tensor maps ----
+  const size_t n_chunks_total = t.chunks.size();
+  SVS_CUDA_TRY(cudaMalloc(&t.d_chunks, sizeof(TcChunk) * n_chunks_total));
+  SVS_CUDA_TRY(cudaMalloc(&t.d_src, sizeof(int2) * n_chunks_total));
+  SVS_CUDA_TRY(cudaMemcpyAsync(t.d_chunks, t.chunks.data(), sizeof(TcChunk) * n_chunks_total,
+                               cudaMemcpyHostToDevice, st));
+  SVS_CUDA_TRY(cudaMemcpyAsync(t.d_src, src.data(), sizeof(int2) * n_chunks_total, cudaMemcpyHostToDevice, st));
+  const size_t w_elems = n_chunks_total * t.block_k * n_total;
+  SVS_CUDA_TRY(cudaMalloc(&t.d_weights, w_elems * es));
+  size_t off = 0;
+  for (int ph = 0; ph < t.n_phases; ++ph) {
+    TcPhase& phs = t.phases[ph];
+    phs.b_elem_off = static_cast<int64_t>(off);
+    t.k_total[ph] = phs.n_chunks * t.block_k;
+    const size_t n = static_cast<size_t>(n_total) * t.k_total[ph];
+    // B tensor map: [Cout][K] K-major
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(t.k_total[ph]), static_cast<cuuint64_t>(n_total)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(t.k_total[ph]) * es};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(t.block_k), static_cast<cuuint32_t>(t.block_n)};
+    int rc = encode_tensor_map(&t.tmap_b[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides, box,
+                               t.swz);
+    if (rc != SVS_OK) return rc;
+    t.tmap_b_wide[ph] = t.tmap_b[ph];
+    if (!t.merged && t.block_n == 128 && t.swz == 128 && n_total % 256 == 0) {
+      const cuuint32_t box_wide[2] = {static_cast<cuuint32_t>(t.block_k), 256u};
+      rc = encode_tensor_map(&t.tmap_b_wide[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides,
+                             box_wide, t.swz);
+      if (rc != SVS_OK) return rc;
+      t.has_wide = true;
+    }
+    off += n;
+  }
+  for (int ph = t.n_phases; ph < 4; ++ph) { t.tmap_b[ph] = t.tmap_b[0]; t.tmap_b_wide[ph] = t.tmap_b_wide[0]; }
+  SVS_CUDA_TRY(cudaStreamSynchronize(st));     // the host vectors are consumed
+  if (w_fold) {
+    int rc = tc_pack_one(t, w_fold, tf32, st);
+    if (rc != SVS_OK) return rc;
+  }
+  t.enabled = true;
+  return SVS_OK;
+}
+
+void tc_free_one(TcLayer& t) {
+  if (t.d_chunks) cudaFree(t.d_chunks);
+  if (t.d_src) cudaFree(t.d_src);
+  if (t.d_weights) cudaFree(t.d_weights);
+  t.d_chunks = nullptr; t.d_src = nullptr; t.d_weights = nullptr; t.enabled = false;
+}
+
 int tc_plan_layers(svs_unet_plan* plan, cudaStream_t st) {
   const bool tf32 = plan->precision == SVS_PRECISION_TF32;
-  const int es = plan->elem_size;
   const unsigned disable = tc_disable_mask();
   for (int li = 1; li <= 10; ++li) {
-    const LayerGeom& g = kLayers[li];
     TcLayer& t = plan->tc[li];
     t.layer = li;
-    int swz = g.cin * es >= 128 ? 128 : g.cin * es;     // one swizzle row = min(128 B, all input channels)
-    if (swz < 32 || (disable >> li) & 1u) continue;     // conv2 in bf16 would be 32-byte rows: allowed
-    t.swz = swz;
-    t.block_k = swz / es;
-    const char* no_merge = std::getenv("SVS_TC_NO_MERGE");
-    t.merged = g.transposed && 4 * g.cout <= 256 && !(no_merge && no_merge[0] == '1');
-    const int n_total = t.merged ? 4 * g.cout : g.cout;
-    t.block_n = n_total < 256 ? (n_total < 128 ? n_total : 128) : (t.merged ? 256 : 128);
-    t.gw = g.transposed ? g.win : g.wout;
-    t.gh = g.transposed ? g.hin : g.hout;
-    t.bw = t.gw < 16 ? t.gw : 16;
-    t.bh = t.gh < 128 / t.bw ? t.gh : 128 / t.bw;
-    t.nb = 128 / (t.bw * t.bh);
-    // ---- K-chunk schedule ----
-    std::vector<int2> src;
-    const int ct = kBufGeom[g.in_buf].c;
-    t.chunks.clear();
-    if (!g.transposed) {
-      t.n_phases = 1;
-      t.phases[0] = TcPhase{0, 0, 0, 0, 0};
-      for (int kh = 0; kh < 5; ++kh)
-        for (int kw = 0; kw < 5; ++kw) {
-          const int qh = kh - 2, qw = kw - 2;
-          const int ph = qh & 1, pw = qw & 1;
-          const int dh = (qh - ph) / 2, dw = (qw - pw) / 2;
-          for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
-            t.chunks.push_back(TcChunk{pw * ct + g.in_coff + c0, dw, ph, dh});
-            src.push_back(make_int2(kh * 5 + kw, c0));
-          }
-        }
-      t.phases[0].n_chunks = static_cast<int>(t.chunks.size());
-    } else if (t.merged) {
-      t.n_phases = 1;
-      t.phases[0] = TcPhase{0, 0, 0, 0, 0};
-      for (int dh = 1; dh >= -1; --dh)
-        for (int dw = 1; dw >= -1; --dw)
-          for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
-            t.chunks.push_back(TcChunk{g.in_coff + c0, dw, 0, dh});
-            src.push_back(make_int2((dh + 1) * 3 + (dw + 1), c0));
-          }
-      t.phases[0].n_chunks = static_cast<int>(t.chunks.size());
-    } else {
-      t.n_phases = 4;
-      for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) {
-          TcPhase& phs = t.phases[py * 2 + px];
-          phs.py = py; phs.px = px;
-          phs.chunk_begin = static_cast<int>(t.chunks.size());
-          for (int kh = py; kh < 5; kh += 2)
-            for (int kw = px; kw < 5; kw += 2) {
-              const int dh = (py + 2 - kh) / 2, dw = (px + 2 - kw) / 2;
-              for (int c0 = 0; c0 < g.cin; c0 += t.block_k) {
-                t.chunks.push_back(TcChunk{g.in_coff + c0, dw, 0, dh});
-                src.push_back(make_int2(kh * 5 + kw, c0));
-              }
-            }
-          phs.n_chunks = static_cast<int>(t.chunks.size()) - phs.chunk_begin;
-        }
-    }
-    // ---- upload schedule, pack weights ----
-    const size_t n_chunks_total = t.chunks.size();
-    int2* d_src = nullptr;
-    SVS_CUDA_TRY(cudaMalloc(&t.d_chunks, sizeof(TcChunk) * n_chunks_total));
-    SVS_CUDA_TRY(cudaMalloc(&d_src, sizeof(int2) * n_chunks_total));
-    SVS_CUDA_TRY(cudaMemcpyAsync(t.d_chunks, t.chunks.data(), sizeof(TcChunk) * n_chunks_total,
-                                 cudaMemcpyHostToDevice, st));
-    SVS_CUDA_TRY(cudaMemcpyAsync(d_src, src.data(), sizeof(int2) * n_chunks_total, cudaMemcpyHostToDevice, st));
-    const size_t w_elems = n_chunks_total * t.block_k * n_total;
-    SVS_CUDA_TRY(cudaMalloc(&t.d_weights, w_elems * es));
-    size_t off = 0;
-    for (int ph = 0; ph < t.n_phases; ++ph) {
-      TcPhase& phs = t.phases[ph];
-      phs.b_elem_off = static_cast<int64_t>(off);
-      t.k_total[ph] = phs.n_chunks * t.block_k;
-      const size_t n = static_cast<size_t>(n_total) * t.k_total[ph];
-      const unsigned blocks = static_cast<unsigned>((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256);
-      if (t.merged && tf32)
-        tc_pack_weights_merged_kernel<float><<<blocks, 256, 0, st>>>(plan->w_fold[li], g.cin, g.cout, d_src,
-                                                                    phs.n_chunks, t.block_k,
-                                                                    static_cast<float*>(t.d_weights));
-      else if (t.merged)
-        tc_pack_weights_merged_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
-            plan->w_fold[li], g.cin, g.cout, d_src, phs.n_chunks, t.block_k,
-            static_cast<__nv_bfloat16*>(t.d_weights));
-      else if (tf32)
-        tc_pack_weights_kernel<float><<<blocks, 256, 0, st>>>(plan->w_fold[li], g.cin, g.cout,
-                                                             d_src + phs.chunk_begin, phs.n_chunks, t.block_k,
-                                                             static_cast<float*>(t.d_weights) + off);
-      else
-        tc_pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
-            plan->w_fold[li], g.cin, g.cout, d_src + phs.chunk_begin, phs.n_chunks, t.block_k,
-            static_cast<__nv_bfloat16*>(t.d_weights) + off);
-      SVS_CHECK_LAUNCH("tc_pack_weights_kernel");
-      // B tensor map: [Cout][K] K-major
-      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(t.k_total[ph]), static_cast<cuuint64_t>(n_total)};
-      const cuuint64_t strides[1] = {static_cast<cuuint64_t>(t.k_total[ph]) * es};
-      const cuuint32_t box[2] = {static_cast<cuuint32_t>(t.block_k), static_cast<cuuint32_t>(t.block_n)};
-      int rc = encode_tensor_map(&t.tmap_b[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides, box,
-                          t.swz);
-      if (rc != SVS_OK) return rc;
-      t.tmap_b_wide[ph] = t.tmap_b[ph];
-      if (!t.merged && t.block_n == 128 && t.swz == 128 && n_total % 256 == 0) {
-        const cuuint32_t box_wide[2] = {static_cast<cuuint32_t>(t.block_k), 256u};
-        rc = encode_tensor_map(&t.tmap_b_wide[ph], tf32, 2, static_cast<char*>(t.d_weights) + off * es, dims, strides,
-                               box_wide, t.swz);
-        if (rc != SVS_OK) return rc;
-        t.has_wide = true;
-      }
-      off += n;
-    }
-    for (int ph = t.n_phases; ph < 4; ++ph) { t.tmap_b[ph] = t.tmap_b[0]; t.tmap_b_wide[ph] = t.tmap_b_wide[0]; }
-    SVS_CUDA_TRY(cudaStreamSynchronize(st));     // d_src / host vectors are consumed
-    SVS_CUDA_TRY(cudaFree(d_src));
-    t.enabled = true;
+    if ((disable >> li) & 1u) continue;
+    int rc = tc_plan_one(t, desc_of_layer(li), plan->w_fold[li], tf32, st);
+    if (rc != SVS_OK) return rc;
   }
   return SVS_OK;
 }
 
 void tc_free_layers(svs_unet_plan* plan) {
-  for (int li = 0; li < 12; ++li) {
-    TcLayer& t = plan->tc[li];
-    if (t.d_chunks) cudaFree(t.d_chunks);
-    if (t.d_weights) cudaFree(t.d_weights);
-    t.d_chunks = nullptr; t.d_weights = nullptr; t.enabled = false;
-  }
+  for (int li = 0; li < 12; ++li) tc_free_one(plan->tc[li]);
 }
 
 // SVS_TC_CLUSTER: 0 = one CTA per tile stream + split-K finish kernel,
@@ -556,11 +601,12 @@ int tc_cluster_mode() {
   static const int mode = [] { const char* e = std::getenv("SVS_TC_CLUSTER"); return e ? std::atoi(e) : 2; }();
   return mode;
 }
-bool ck_supported(const svs_unet_plan* plan, int li, int split);
-int ck_launch_layer(const svs_unet_plan* plan, int li, const CUtensorMap& ta, const TcParams& p, cudaStream_t st);
+bool ck_supported(const TcLayer& t, int split);
+int ck_launch_layer(const TcLayer& t, bool tf32, const CUtensorMap& ta, const TcParams& p, cudaStream_t st);
 
-// Tiling of one layer at one batch size: M tiles, the N tile (a layer with has_wide may use 256) and split-K.
-void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, int* split_k, int* block_n) {
+// Tiling of one problem at one batch size: M tiles, the N tile (a layer with has_wide may use 256) and split-K.
+void tc_tiling(const TcLayer& t, int batch, int* m_tiles, int* split_k, int* block_n) {
+  const ConvDesc& g = t.d;
   const int ntw = t.gw / t.bw, nth = t.gh / t.bh, ntb = (batch + t.nb - 1) / t.nb;
   *m_tiles = ntw * nth * ntb;
   *block_n = t.block_n;
@@ -590,25 +636,27 @@ void tc_tiling(const TcLayer& t, const LayerGeom& g, int batch, int* m_tiles, in
   }
 }
 
+size_t tc_splitk_bytes_one(const TcLayer& t, int batch) {
+  if (!t.enabled) return 0;
+  int m_tiles, split, block_n;
+  tc_tiling(t, batch, &m_tiles, &split, &block_n);
+  if (split <= 1) return 0;
+  return static_cast<size_t>(split) * t.n_phases * m_tiles * 128 * t.d.cout * sizeof(float);
+}
+
 size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch) {
   size_t best = 0;
   for (int li = 0; li < 12; ++li) {
-    const TcLayer& t = plan->tc[li];
-    if (!t.enabled) continue;
-    int m_tiles, split, block_n;
-    tc_tiling(t, kLayers[li], batch, &m_tiles, &split, &block_n);
-    if (split > 1) {
-      const size_t bytes = static_cast<size_t>(split) * t.n_phases * m_tiles * 128 * kLayers[li].cout * sizeof(float);
-      best = bytes > best ? bytes : best;
-    }
+    const size_t bytes = tc_splitk_bytes_one(plan->tc[li], batch);
+    best = bytes > best ? bytes : best;
   }
   return best;
 }
 
 int tc_launch_count(const svs_unet_plan* plan, int li, int batch) {
   int m_tiles, split, block_n;
-  tc_tiling(plan->tc[li], kLayers[li], batch, &m_tiles, &split, &block_n);
-  if (split > 1 && tc_cluster_mode() == 2 && ck_supported(plan, li, split)) return 1;
+  tc_tiling(plan->tc[li], batch, &m_tiles, &split, &block_n);
+  if (split > 1 && tc_cluster_mode() == 2 && ck_supported(plan->tc[li], split)) return 1;
   return split > 1 ? 2 : 1;   // main kernel (+ split-K reduction)
 }
 
@@ -632,25 +680,24 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap* tb, const TcParam
 long long* g_tc_dbg = nullptr;   // set through svs_debug_set_trace (profiling only)
 int g_tc_dbg_layer = -1;
 
-int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st) {
-  const TcLayer& t = plan->tc[li];
-  const LayerGeom& g = kLayers[li];
-  const bool tf32 = plan->precision == SVS_PRECISION_TF32;
-  const int es = plan->elem_size;
+// Enqueues one planned problem on `io`'s buffers.
+int tc_launch(const TcLayer& t, const TcIo& io, int batch, bool tf32, cudaStream_t st) {
+  const ConvDesc& g = t.d;
+  const int es = tf32 ? 4 : 2;
   static std::mutex mu;
   CUtensorMap ta;
   {
     std::lock_guard<std::mutex> lock(mu);
     int hit = -1;
     for (int i = 0; i < TcLayer::kTmapCache; ++i)
-      if (t.tmap_a_base[i] == ws.buf[g.in_buf] && t.tmap_a_batch[i] == batch) hit = i;
+      if (t.tmap_a_base[i] == io.in && t.tmap_a_batch[i] == batch) hit = i;
     if (hit < 0) {
       hit = t.tmap_a_next;
       t.tmap_a_next = (t.tmap_a_next + 1) % TcLayer::kTmapCache;
       t.tmap_a_base[hit] = nullptr;
-      int rc = make_tmap_a(t, g, ws.buf[g.in_buf], batch, es, tf32, &t.tmap_a[hit]);
+      int rc = make_tmap_a(t, io.in, batch, es, tf32, &t.tmap_a[hit]);
       if (rc != SVS_OK) return rc;
-      t.tmap_a_base[hit] = ws.buf[g.in_buf];
+      t.tmap_a_base[hit] = io.in;
       t.tmap_a_batch[hit] = batch;
     }
     ta = t.tmap_a[hit];
@@ -664,7 +711,7 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     p.px[ph] = t.phases[ph < t.n_phases ? ph : 0].px;
   }
   int m_tiles, split, block_n;
-  tc_tiling(t, g, batch, &m_tiles, &split, &block_n);
+  tc_tiling(t, batch, &m_tiles, &split, &block_n);
   const CUtensorMap* tb = block_n == t.block_n ? t.tmap_b : t.tmap_b_wide;
   p.n_phases = t.n_phases;
   p.split_k = split;
@@ -673,29 +720,30 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   p.bw_log2 = ilog2_exact(t.bw); p.bh_log2 = ilog2_exact(t.bh);
   p.batch = batch;
   p.block_k = t.block_k;
-  p.out = ws.buf[g.out_buf];
-  p.out_pitch = kBufGeom[g.out_buf].c;
+  p.out = io.out;
+  p.out_pitch = g.out_pitch;
   p.out_coff = g.out_coff;
   p.hout = g.hout; p.wout = g.wout;
   p.out_scale = g.transposed ? 2 : 1;
-  p.bias = plan->b_fold[li];
+  p.bias = io.bias;
   p.act = g.act;
-  p.partial = ws.splitk;
+  p.out_flags = io.out_flags;
+  p.partial = io.splitk;
   p.m_pad = m_tiles * 128;
   p.cout = t.merged ? 4 * g.cout : g.cout;
   p.merged = t.merged ? 1 : 0;
   p.cout_phase = g.cout;
-  p.dbg = (g_tc_dbg_layer == li) ? g_tc_dbg : nullptr;
-  if (split > 1 && ws.splitk_bytes < static_cast<size_t>(split) * t.n_phases * p.m_pad * g.cout * sizeof(float))
-    return fail(SVS_ERR_WORKSPACE, "tc_launch_layer: split-K scratch too small");
+  p.dbg = io.dbg;
   p.m_tiles = m_tiles;
   p.n_tiles = p.cout / block_n;
   const int grid = m_tiles * p.n_tiles * t.n_phases * split;
   int rc = SVS_ERR_NOT_IMPLEMENTED;
   bool finish = split > 1;
-  if (tc_cluster_mode() == 2 && split > 1 && ck_supported(plan, li, split)) {
-    rc = ck_launch_layer(plan, li, ta, p, st);          // split-K inside a cluster: no partials, no finish kernel
+  if (tc_cluster_mode() == 2 && split > 1 && ck_supported(t, split)) {
+    rc = ck_launch_layer(t, tf32, ta, p, st);           // split-K inside a cluster: no partials, no finish kernel
     finish = false;
+  } else if (split > 1 && io.splitk_bytes < static_cast<size_t>(split) * t.n_phases * p.m_pad * g.cout * sizeof(float)) {
+    return fail(SVS_ERR_WORKSPACE, "tc_launch: split-K scratch too small");
   }
 #define SVS_TC_CASE(N, S, ST)                                                                       \
   if (rc == SVS_ERR_NOT_IMPLEMENTED && block_n == N && t.swz == S) { \
@@ -707,12 +755,13 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   SVS_TC_CASE(64, 128, 4)
   SVS_TC_CASE(32, 128, 4)
   SVS_TC_CASE(16, 128, 4)
+  SVS_TC_CASE(128, 64, 4)
   SVS_TC_CASE(64, 64, 4)
   SVS_TC_CASE(32, 64, 4)
   SVS_TC_CASE(32, 32, 4)
 #undef SVS_TC_CASE
   if (rc == SVS_ERR_NOT_IMPLEMENTED)
-    return fail(rc, "tc_launch_layer: no kernel instantiation for block_n=" + std::to_string(block_n) +
+    return fail(rc, "tc_launch: no kernel instantiation for block_n=" + std::to_string(block_n) +
                         " swz=" + std::to_string(t.swz));
   if (rc != SVS_OK) return rc;
   if (finish) {
@@ -722,6 +771,18 @@ int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     else SVS_CUDA_TRY(launch_pdl(splitk_finish_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, p));
   }
   return SVS_OK;
+}
+
+int tc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st) {
+  const LayerGeom& g = kLayers[li];
+  TcIo io;
+  io.in = ws.buf[g.in_buf];
+  io.out = ws.buf[g.out_buf];
+  io.bias = plan->b_fold[li];
+  io.splitk = ws.splitk;
+  io.splitk_bytes = ws.splitk_bytes;
+  io.dbg = (g_tc_dbg_layer == li) ? g_tc_dbg : nullptr;
+  return tc_launch(plan->tc[li], io, batch, plan->precision == SVS_PRECISION_TF32, st);
 }
 
 }  // namespace svs

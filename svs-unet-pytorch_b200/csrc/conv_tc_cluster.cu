@@ -64,9 +64,16 @@ __device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&o)[4]) 
   u.y = *reinterpret_cast<uint32_t*>(&c);
   *reinterpret_cast<uint2*>(dst) = u;
 }
-__device__ __forceinline__ void store4(float* dst, const float (&o)[4]) {
-  *reinterpret_cast<float4*>(dst) = make_float4(round_tf32(o[0]), round_tf32(o[1]), round_tf32(o[2]), round_tf32(o[3]));
+__device__ __forceinline__ void store4(float* dst, const float (&o)[4], int out_flags = 0) {
+  float4 r = make_float4(o[0], o[1], o[2], o[3]);
+  if (out_flags & OUT_ACCUMULATE) {
+    const float4 old = *reinterpret_cast<const float4*>(dst);
+    r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+  }
+  if (!(out_flags & OUT_KEEP_FP32)) r = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
+  *reinterpret_cast<float4*>(dst) = r;
 }
+__device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&o)[4], int) { store4(dst, o); }
 
 template <typename OutT, bool kTf32, int kSplit>
 __global__ void __launch_bounds__(kTcThreads)
@@ -238,7 +245,7 @@ tc_conv_ck_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const float t[4] = {acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w};
         const float o[4] = {fmaxf(t[0], fmaf(slope, t[0], 0.0f)), fmaxf(t[1], fmaf(slope, t[1], 0.0f)),
                             fmaxf(t[2], fmaf(slope, t[2], 0.0f)), fmaxf(t[3], fmaf(slope, t[3], 0.0f))};
-        if (b < p.batch) store4(out_n + static_cast<size_t>((b * p.hout + oy) * p.wout + ox) * pix_pitch, o);
+        if (b < p.batch) store4(out_n + static_cast<size_t>((b * p.hout + oy) * p.wout + ox) * pix_pitch, o, p.out_flags);
       }
     }
   }
@@ -254,8 +261,7 @@ tc_conv_ck_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-bool ck_supported(const svs_unet_plan* plan, int li, int split) {
-  const TcLayer& t = plan->tc[li];
+bool ck_supported(const TcLayer& t, int split) {
   const bool pow2 = !(t.bw & (t.bw - 1)) && !(t.bh & (t.bh - 1));     // pixel decode by shifts in the reduction
   return t.enabled && !t.merged && pow2 && t.swz == 128 && t.block_n == 128 && (split == 2 || split == 4 || split == 8);
 }
@@ -280,9 +286,7 @@ static int launch_ck(const CUtensorMap& ta, const TcLayer& t, const TcParams& p,
   return SVS_OK;
 }
 
-int ck_launch_layer(const svs_unet_plan* plan, int li, const CUtensorMap& ta, const TcParams& p, cudaStream_t st) {
-  const TcLayer& t = plan->tc[li];
-  const bool tf32 = plan->precision == SVS_PRECISION_TF32;
+int ck_launch_layer(const TcLayer& t, bool tf32, const CUtensorMap& ta, const TcParams& p, cudaStream_t st) {
 #define SVS_CK_CASE(S)                                                                     \
   if (p.split_k == S)                                                                      \
     return tf32 ? launch_ck<float, true, S>(ta, t, p, st) : launch_ck<__nv_bfloat16, false, S>(ta, t, p, st);

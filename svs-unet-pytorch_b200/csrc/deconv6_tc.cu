@@ -267,16 +267,22 @@ void d6_free(svs_unet_plan* plan) {
   plan->d6_enabled = false;
 }
 
-int d6_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_view* in, const svs_patch_view* out,
-              const int32_t* in_frames, int batch, int flags, cudaStream_t st) {
-  const bool tf32 = plan->precision == SVS_PRECISION_TF32;
-  const int es = plan->elem_size;
+// (re)pack the [25][32] folded weights into the taps-as-N operand (training repacks every step)
+int d6_pack(const float* w_fold, bool tf32, void* d6_weights, cudaStream_t st) {
+  d6_pack_weights_kernel<<<4, 256, 0, st>>>(w_fold, tf32 ? 1 : 0, d6_weights);
+  SVS_CHECK_LAUNCH("d6_pack_weights_kernel");
+  return SVS_OK;
+}
+
+int d6_launch_raw(bool tf32, const CUtensorMap& tmap_w, const float* bias, const void* cat1, const svs_patch_view* in,
+                  const svs_patch_view* out, const int32_t* in_frames, int batch, int flags, cudaStream_t st) {
+  const int es = tf32 ? 4 : 2;
   CUtensorMap ta;
   const cuuint64_t dims[4] = {32, 64, 256, static_cast<cuuint64_t>(batch)};
   const cuuint64_t strides[3] = {static_cast<cuuint64_t>(32 * es), static_cast<cuuint64_t>(64 * 32 * es),
                                  static_cast<cuuint64_t>(256) * 64 * 32 * es};
   const cuuint32_t box[4] = {32, 64, kD6Rows, 1};
-  int rc = encode_tensor_map(&ta, tf32, 4, ws.buf[BUF_CAT1], dims, strides, box, 32 * es);
+  int rc = encode_tensor_map(&ta, tf32, 4, const_cast<void*>(cat1), dims, strides, box, 32 * es);
   if (rc != SVS_OK) return rc;
   dim3 grid((256 + kD6Interior - 1) / kD6Interior, batch);
   auto dense_view = [](const svs_patch_view* v) {
@@ -287,16 +293,30 @@ int d6_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_vi
   const bool dense = dense_view(in) && dense_view(out);
   auto launch = [&](auto kern, size_t smem) -> int {
     SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    SVS_CUDA_TRY(launch_pdl(kern, grid, dim3(kD6Threads), smem, st, ta, plan->d6_tmap_w,
-                            static_cast<const float*>(plan->b_fold[11]), static_cast<const float*>(in->base),
-                            in->patch_off, in->stride_b, in->stride_f, in->stride_t, out->base, out->patch_off,
-                            out->stride_b, out->stride_f, out->stride_t, in_frames, flags));
+    SVS_CUDA_TRY(launch_pdl(kern, grid, dim3(kD6Threads), smem, st, ta, tmap_w, bias,
+                            static_cast<const float*>(in->base), in->patch_off, in->stride_b, in->stride_f,
+                            in->stride_t, out->base, out->patch_off, out->stride_b, out->stride_f, out->stride_t,
+                            in_frames, flags));
     return SVS_OK;
   };
   if (tf32) return dense ? launch(deconv6_tc_kernel<true, 128, true>, d6_smem_bytes<128>())
                          : launch(deconv6_tc_kernel<true, 128, false>, d6_smem_bytes<128>());
   return dense ? launch(deconv6_tc_kernel<false, 64, true>, d6_smem_bytes<64>())
                : launch(deconv6_tc_kernel<false, 64, false>, d6_smem_bytes<64>());
+}
+
+int d6_make_weight_map(void* d6_weights, bool tf32, CUtensorMap* out) {
+  const int es = tf32 ? 4 : 2;
+  const cuuint64_t dims[2] = {32, 32};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(32 * es)};
+  const cuuint32_t box[2] = {32, 32};
+  return encode_tensor_map(out, tf32, 2, d6_weights, dims, strides, box, 32 * es);
+}
+
+int d6_launch(const svs_unet_plan* plan, const Workspace& ws, const svs_patch_view* in, const svs_patch_view* out,
+              const int32_t* in_frames, int batch, int flags, cudaStream_t st) {
+  return d6_launch_raw(plan->precision == SVS_PRECISION_TF32, plan->d6_tmap_w,
+                       static_cast<const float*>(plan->b_fold[11]), ws.buf[BUF_CAT1], in, out, in_frames, batch, flags, st);
 }
 
 }  // namespace svs

@@ -24,6 +24,7 @@ struct TcParams {
   int out_pitch, out_coff, hout, wout, out_scale;
   const float* bias;
   int act;
+  int out_flags;                 // OutFlags: accumulate into the output / keep fp32 outputs unrounded
   float* partial;
   int m_pad;                     // rows per (phase, split) slab of `partial`
   int cout;                      // GEMM N (merged deconv: 4 x channels)

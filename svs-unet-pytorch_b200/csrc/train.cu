@@ -3,11 +3,20 @@
 // Replaces the autograd graph of reference train.py:274-299 / model.py:203-220.  Activations are
 // fp32 NHWC in the same concat-buffer layout as the inference path; every reduction (BatchNorm
 // statistics, bias / BatchNorm gradients, weight gradients, the loss) is two-stage with a fixed order,
-// so a step is bit-reproducible (no atomics).  Convolutions run on the fp32 CUDA-core kernels of
-// conv_direct.cu:  dgrad of a stride-2 conv is the transposed-conv kernel with channel-transposed
-// weights, dgrad of a transposed conv is the conv kernel, wgrad is the pixel-reduction GEMM below.
-// (The tensor-core forward kernels are inference-only for now: see DESIGN.md "next".)
+// so a step is bit-reproducible (no atomics).
+//
+// Two arithmetic modes, selected by the `plan` argument of the C ABI:
+//   plan != NULL (svs_unet_train_plan_create): TF32 on tcgen05.  Forward and data-gradient convolutions are the
+//     implicit-GEMM kernels of conv_tc.cu / conv_tc_cluster.cu (kind::tf32, fp32 accumulate; dgrad of a stride-2 conv
+//     is the transposed-conv kernel with channel-transposed weights and vice versa), the weight gradient is the
+//     MN-major pixel-reduction GEMM of wgrad_tc.cu.  Operands are rounded to TF32 where they are produced
+//     (BatchNorm apply / BatchNorm backward); statistics, normalisation, loss and all reductions stay fp32.
+//   plan == NULL: exact fp32 on the CUDA-core kernels of conv_direct.cu (parity mode).
+// conv1 (Cin = 1) and deconv6 (Cout = 1) are memory-bound edge layers with CUDA-core kernels in both modes.
 #include "unet_internal.cuh"
+#include "tc_ptx.cuh"
+
+#include <new>
 
 namespace svs {
 
@@ -20,7 +29,23 @@ int launch_deconv6_f32(const float* cat1, const float* w, const float* bias, flo
 
 constexpr float kBnEps = 1e-5f;
 constexpr float kBnMomentum = 0.1f;
-constexpr int kRedSplits = 64;                   // stage-1 partial sums per channel
+constexpr int kRedSplits = 64;                   // stage-1 partial sums per channel (fp32 parity mode)
+constexpr int kRedBlocksMax = 1184;              // stage-1 blocks of the row-streaming reduction (8 per SM)
+
+// conv_tc.cu / wgrad_tc.cu
+int tc_plan_one(TcLayer& t, const ConvDesc& g, const float* w_fold, bool tf32, cudaStream_t st);
+int tc_pack_one(TcLayer& t, const float* w_fold, bool tf32, cudaStream_t st);
+void tc_free_one(TcLayer& t);
+int tc_launch(const TcLayer& t, const TcIo& io, int batch, bool tf32, cudaStream_t st);
+size_t tc_splitk_bytes_one(const TcLayer& t, int batch);
+int d6_pack(const float* w_fold, bool tf32, void* d6_weights, cudaStream_t st);
+int d6_make_weight_map(void* d6_weights, bool tf32, CUtensorMap* out);
+int d6_launch_raw(bool tf32, const CUtensorMap& tmap_w, const float* bias, const void* cat1, const svs_patch_view* in,
+                  const svs_patch_view* out, const int32_t* in_frames, int batch, int flags, cudaStream_t st);
+bool wgrad_tc_supported(int gh, int gw, int s_c, int l_c, int s_pitch, int l_pitch, int s_coff, int l_coff);
+size_t wgrad_tc_partial_floats(int gh, int gw, int batch, int s_c, int l_c);
+int wgrad_tc_launch(const float* S, int s_pitch, int s_coff, int s_c, const float* L, int l_pitch, int l_coff, int l_c,
+                    int gh, int gw, int batch, float* partial, size_t partial_floats, float* grad_w, cudaStream_t st);
 
 // torch layout -> [tap][ci][co]  (conv: (co,ci,kh,kw); deconv: (ci,co,kh,kw)) and its channel transpose
 __global__ void train_pack_kernel(const float* __restrict__ w, int cin, int cout, int transposed,
@@ -93,13 +118,83 @@ channel_reduce_kernel(RedArgs a, float* __restrict__ partial /*[splits][2][C]*/)
   }
 }
 
+// Row-streaming form of the same two reductions: a CTA walks a contiguous run of pixels, thread = (4-channel group,
+// row lane), 16-byte loads, so a warp reads whole rows and the pass runs at HBM speed (the column-strided kernel
+// above keeps 64 CTAs busy and costs 0.2 - 0.6 ms per layer at batch 64).  Row lanes are added in fixed order and
+// every CTA writes one partial -> deterministic.  Requires C % 4 == 0, C <= 1024, pitches / offsets % 4 == 0.
+template <int kMode>
+__global__ void __launch_bounds__(256)
+channel_reduce_rows_kernel(RedArgs a, int pix_log2, float* __restrict__ partial /*[gridDim.x][2][C]*/) {
+  __shared__ float4 s0[256], s1[256];
+  const int cgs = a.C >> 2;                                   // 4-channel groups per row (<= 256)
+  const int rows = 256 / cgs;                                 // rows per iteration
+  const int cg = threadIdx.x % cgs, rl = threadIdx.x / cgs;
+  size_t per = (a.N + gridDim.x - 1) / gridDim.x;
+  per = (per + rows - 1) / rows * rows;
+  const size_t n0 = blockIdx.x * per, n1 = min(a.N, n0 + per);
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  float4 mean4 = acc0, istd4 = acc0;
+  if (kMode == 1 && rl < rows) {
+    mean4 = *reinterpret_cast<const float4*>(a.mean + 4 * cg);
+    istd4 = *reinterpret_cast<const float4*>(a.invstd + 4 * cg);
+  }
+  if (rl < rows) {
+    for (size_t n = n0 + rl; n < n1; n += rows) {
+      const float4 z = *reinterpret_cast<const float4*>(a.z + n * a.C + 4 * cg);
+      if (kMode == 0) {
+        acc0.x += z.x; acc0.y += z.y; acc0.z += z.z; acc0.w += z.w;
+        acc1.x += z.x * z.x; acc1.y += z.y * z.y; acc1.z += z.z * z.z; acc1.w += z.w * z.w;
+      } else {
+        const size_t o = n * a.y_pitch + a.y_coff + 4 * cg;
+        const float4 yv = *reinterpret_cast<const float4*>(a.y + o);
+        float4 g = *reinterpret_cast<const float4*>(a.dy + o);
+        if (a.keep) {
+          const uchar4 k = *reinterpret_cast<const uchar4*>(a.keep + (n >> pix_log2) * a.C + 4 * cg);
+          g.x = k.x ? 2.0f * g.x : 0.0f; g.y = k.y ? 2.0f * g.y : 0.0f;
+          g.z = k.z ? 2.0f * g.z : 0.0f; g.w = k.w ? 2.0f * g.w : 0.0f;
+        }
+        const float neg = a.act == ACT_LEAKY ? 0.2f : 0.0f;   // ACT_RELU: 0
+        g.x = yv.x > 0.f ? g.x : neg * g.x; g.y = yv.y > 0.f ? g.y : neg * g.y;
+        g.z = yv.z > 0.f ? g.z : neg * g.z; g.w = yv.w > 0.f ? g.w : neg * g.w;
+        acc0.x += g.x; acc0.y += g.y; acc0.z += g.z; acc0.w += g.w;
+        acc1.x += g.x * ((z.x - mean4.x) * istd4.x); acc1.y += g.y * ((z.y - mean4.y) * istd4.y);
+        acc1.z += g.z * ((z.z - mean4.z) * istd4.z); acc1.w += g.w * ((z.w - mean4.w) * istd4.w);
+      }
+    }
+  }
+  s0[threadIdx.x] = acc0; s1[threadIdx.x] = acc1;
+  __syncthreads();
+  if (threadIdx.x < cgs) {
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    for (int r = 0; r < rows; ++r) {                          // fixed order
+      const float4 u = s0[r * cgs + cg], v = s1[r * cgs + cg];
+      t0.x += u.x; t0.y += u.y; t0.z += u.z; t0.w += u.w;
+      t1.x += v.x; t1.y += v.y; t1.z += v.z; t1.w += v.w;
+    }
+    *reinterpret_cast<float4*>(partial + (static_cast<size_t>(blockIdx.x) * 2 + 0) * a.C + 4 * cg) = t0;
+    *reinterpret_cast<float4*>(partial + (static_cast<size_t>(blockIdx.x) * 2 + 1) * a.C + 4 * cg) = t1;
+  }
+}
+
+// fixed-order sum of partial[i * stride] over i < splits by one warp: lanes stride over the partials in double,
+// then a shuffle tree (the same tree every run -> deterministic)
+__device__ __forceinline__ double warp_sum_partials(const float* __restrict__ partial, int splits, size_t stride, int lane) {
+  double s = 0.0;
+  for (int i = lane; i < splits; i += 32) s += static_cast<double>(partial[i * stride]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// one warp per channel
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int splits, int C, double n,
                                    float* __restrict__ mean, float* __restrict__ invstd,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, int update) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int i = 0; i < splits; ++i) { s += partial[(i * 2 + 0) * C + c]; ss += partial[(i * 2 + 1) * C + c]; }
+  const double s = warp_sum_partials(partial + c, splits, static_cast<size_t>(2) * C, lane);
+  const double ss = warp_sum_partials(partial + C + c, splits, static_cast<size_t>(2) * C, lane);
+  if (lane != 0) return;
   const double m = s / n;
   double var = ss / n - m * m;
   if (var < 0.0) var = 0.0;
@@ -115,7 +210,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int splits
 __global__ void bn_apply_kernel(const float* __restrict__ z, size_t N, int C, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const uint8_t* __restrict__ keep,
-                                int pix_per_sample, int act, float* __restrict__ y, int y_pitch, int y_coff) {
+                                int pix_per_sample, int act, float* __restrict__ y, int y_pitch, int y_coff,
+                                int round_to_tf32) {
   const size_t total = N * C;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -125,7 +221,82 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, size_t N, int C, co
     if (act == ACT_LEAKY) v = v > 0.f ? v : 0.2f * v;
     else if (act == ACT_RELU) v = fmaxf(v, 0.f);
     if (keep) v = keep[(n / pix_per_sample) * C + c] ? 2.0f * v : 0.0f;
-    y[n * y_pitch + y_coff + c] = v;
+    y[n * y_pitch + y_coff + c] = round_to_tf32 ? round_tf32(v) : v;         // operand of the next layer's MMAs
+  }
+}
+
+// 16-byte forms of the two elementwise BatchNorm passes (C a power of two >= 4, pitches / offsets % 4 == 0, pixels per
+// sample a power of two): index math by shifts instead of 64-bit divisions, four channels per thread
+__global__ void __launch_bounds__(256)
+bn_apply_vec_kernel(const float4* __restrict__ z, size_t n4, int cg_log2, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const uint8_t* __restrict__ keep, int pix_log2, int act, float* __restrict__ y, int y_pitch,
+                    int y_coff, int round_to_tf32) {
+  const int cg_mask = (1 << cg_log2) - 1;
+  const float neg = act == ACT_LEAKY ? 0.2f : (act == ACT_RELU ? 0.0f : 1.0f);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i) & cg_mask;
+    const size_t n = i >> cg_log2;
+    const float4 v = z[i];
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cg), s = __ldg(reinterpret_cast<const float4*>(invstd) + cg);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + cg), b = __ldg(reinterpret_cast<const float4*>(beta) + cg);
+    float o[4] = {(v.x - m.x) * s.x * g.x + b.x, (v.y - m.y) * s.y * g.y + b.y, (v.z - m.z) * s.z * g.z + b.z,
+                  (v.w - m.w) * s.w * g.w + b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = o[k] > 0.f ? o[k] : neg * o[k];
+    if (keep) {
+      const uchar4 kp = *reinterpret_cast<const uchar4*>(keep + (((n >> pix_log2) << (cg_log2 + 2)) + 4 * cg));
+      o[0] = kp.x ? 2.0f * o[0] : 0.0f; o[1] = kp.y ? 2.0f * o[1] : 0.0f;
+      o[2] = kp.z ? 2.0f * o[2] : 0.0f; o[3] = kp.w ? 2.0f * o[3] : 0.0f;
+    }
+    if (round_to_tf32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = round_tf32(o[k]);
+    }
+    *reinterpret_cast<float4*>(y + n * y_pitch + y_coff + 4 * cg) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec_kernel(RedArgs a, int cg_log2, int pix_log2, const float* __restrict__ gamma,
+                        const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float4* __restrict__ z_inout,
+                        int round_to_tf32) {
+  const int cg_mask = (1 << cg_log2) - 1;
+  const size_t n4 = (a.N << cg_log2);
+  const float inv_n = 1.0f / static_cast<float>(a.N);
+  const float neg = a.act == ACT_LEAKY ? 0.2f : 0.0f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i) & cg_mask;
+    const size_t n = i >> cg_log2;
+    const size_t o = n * a.y_pitch + a.y_coff + 4 * cg;
+    const float4 yv = *reinterpret_cast<const float4*>(a.y + o);
+    const float4 dy = *reinterpret_cast<const float4*>(a.dy + o);
+    float g[4] = {dy.x, dy.y, dy.z, dy.w};
+    const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
+    if (a.keep) {
+      const uchar4 kp = *reinterpret_cast<const uchar4*>(a.keep + (((n >> pix_log2) << (cg_log2 + 2)) + 4 * cg));
+      g[0] = kp.x ? 2.0f * g[0] : 0.0f; g[1] = kp.y ? 2.0f * g[1] : 0.0f;
+      g[2] = kp.z ? 2.0f * g[2] : 0.0f; g[3] = kp.w ? 2.0f * g[3] : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = yy[k] > 0.f ? g[k] : neg * g[k];
+    const float4 zz = z_inout[i];
+    const float zv[4] = {zz.x, zz.y, zz.z, zz.w};
+    const float4 m = __ldg(reinterpret_cast<const float4*>(a.mean) + cg), s = __ldg(reinterpret_cast<const float4*>(a.invstd) + cg);
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + cg);
+    const float4 sg = __ldg(reinterpret_cast<const float4*>(sum_g) + cg), sx = __ldg(reinterpret_cast<const float4*>(sum_gx) + cg);
+    const float mm[4] = {m.x, m.y, m.z, m.w}, ss[4] = {s.x, s.y, s.z, s.w}, gg[4] = {gm.x, gm.y, gm.z, gm.w};
+    const float s1[4] = {sg.x, sg.y, sg.z, sg.w}, s2[4] = {sx.x, sx.y, sx.z, sx.w};
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (zv[k] - mm[k]) * ss[k];
+      const float dz = gg[k] * ss[k] * (g[k] - s1[k] * inv_n - xh * s2[k] * inv_n);
+      r[k] = round_to_tf32 ? round_tf32(dz) : dz;
+    }
+    z_inout[i] = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -133,10 +304,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int sp
                                        float* __restrict__ sum_g, float* __restrict__ sum_gx,
                                        float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
                                        float* __restrict__ grad_conv_bias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int i = 0; i < splits; ++i) { s += partial[(i * 2 + 0) * C + c]; sx += partial[(i * 2 + 1) * C + c]; }
+  const double s = warp_sum_partials(partial + c, splits, static_cast<size_t>(2) * C, lane);
+  const double sx = warp_sum_partials(partial + C + c, splits, static_cast<size_t>(2) * C, lane);
+  if (lane != 0) return;
   sum_g[c] = static_cast<float>(s);
   sum_gx[c] = static_cast<float>(sx);
   grad_beta[c] = static_cast<float>(s);
@@ -146,7 +318,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int sp
 
 // dz = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)), written in place over z
 __global__ void bn_bwd_apply_kernel(RedArgs a, const float* __restrict__ gamma, const float* __restrict__ sum_g,
-                                    const float* __restrict__ sum_gx, float* __restrict__ z_inout) {
+                                    const float* __restrict__ sum_gx, float* __restrict__ z_inout, int round_to_tf32) {
   const size_t total = a.N * a.C;
   const float inv_n = 1.0f / static_cast<float>(a.N);
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -155,7 +327,8 @@ __global__ void bn_bwd_apply_kernel(RedArgs a, const float* __restrict__ gamma, 
     const size_t n = i / a.C;
     const float g = dy_effective(a, n, c);
     const float xh = (z_inout[i] - a.mean[c]) * a.invstd[c];
-    z_inout[i] = gamma[c] * a.invstd[c] * (g - sum_g[c] * inv_n - xh * sum_gx[c] * inv_n);
+    const float dz = gamma[c] * a.invstd[c] * (g - sum_g[c] * inv_n - xh * sum_gx[c] * inv_n);
+    z_inout[i] = round_to_tf32 ? round_tf32(dz) : dz;                        // operand of the dgrad / wgrad MMAs
   }
 }
 
@@ -302,6 +475,71 @@ wgrad_small_kernel(WgradArgs a, int gw_log2, int gh_log2, int sc_log2, int lc_lo
   }
 }
 
+// ---- weight gradient of the two single-channel edge layers -----------------------------------------
+// conv1  : dW[co][tap] = sum dz[b,y,x,co] * mix[b, 2y+kh-2, 2x+kw-2]     (S = dz, 16 channels; L = the mixture)
+// deconv6: dW[ci][tap] = sum x[b,y,x,ci]  * dz6[b, 2y+kh-2, 2x+kw-2]     (S = cat1, 32 channels; L = dz6)
+// One CTA = one image x 8 rows of the 256 x 64 small grid: the (19 x 131)-sample window of L sits in shared memory,
+// S streams through it one row at a time; thread = (channel, tap group), all lanes of a warp read the same L sample
+// (broadcast).  Every CTA writes one partial [25][C]; wgrad_edge_finalize_kernel adds them in fixed order.  Memory
+// bound (S is read once: 67 / 134 MB per 64 patches) instead of the 25 x re-read of wgrad_small_kernel.
+constexpr int kEdgeRows = 8;
+template <int C>
+__global__ void __launch_bounds__(256)
+wgrad_edge_kernel(const float* __restrict__ S /*[B][256][64][C]*/, const float* __restrict__ L /*[B][512][128]*/,
+                  float* __restrict__ partial /*[gridDim.y * gridDim.x][25][C]*/) {
+  constexpr int kGroups = 256 / C;                       // tap groups: 8 (C = 32) or 16 (C = 16)
+  constexpr int kTaps = (25 + kGroups - 1) / kGroups;    // taps per thread: 4 or 2
+  constexpr int kWinW = 132, kWinH = 2 * kEdgeRows + 3;
+  __shared__ float win[kWinH * kWinW];
+  __shared__ __align__(16) float srow[64 * C];
+  const int b = blockIdx.y, row0 = blockIdx.x * kEdgeRows;
+  const float* Lb = L + static_cast<size_t>(b) * 512 * 128;
+  for (int i = threadIdx.x; i < kWinH * kWinW; i += 256) {
+    const int r = i / kWinW, c = i - r * kWinW;
+    const int ly = 2 * row0 - 2 + r, lx = c - 2;
+    win[i] = (ly >= 0 && ly < 512 && lx >= 0 && lx < 128 && c < 131) ? __ldg(Lb + ly * 128 + lx) : 0.0f;
+  }
+  const int c = threadIdx.x % C, tg = threadIdx.x / C;
+  int off[kTaps];
+  float acc[kTaps];
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) {
+    const int tap = tg + k * kGroups;
+    off[k] = tap < 25 ? (tap / 5) * kWinW + tap % 5 : -1;
+    acc[k] = 0.0f;
+  }
+  const float* Sb = S + (static_cast<size_t>(b) * 256 + row0) * 64 * C;
+  for (int r = 0; r < kEdgeRows; ++r) {
+    __syncthreads();                                     // window ready / previous row consumed
+    const float4* src = reinterpret_cast<const float4*>(Sb + static_cast<size_t>(r) * 64 * C);
+    for (int i = threadIdx.x; i < 64 * C / 4; i += 256) reinterpret_cast<float4*>(srow)[i] = __ldg(src + i);
+    __syncthreads();
+    const float* wrow = win + 2 * r * kWinW;
+#pragma unroll 8
+    for (int x = 0; x < 64; ++x) {
+      const float s = srow[x * C + c];
+#pragma unroll
+      for (int k = 0; k < kTaps; ++k)
+        if (off[k] >= 0) acc[k] = fmaf(s, wrow[off[k] + 2 * x], acc[k]);
+    }
+  }
+  float* dst = partial + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 25 * C;
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) {
+    const int tap = tg + k * kGroups;
+    if (tap < 25) dst[tap * C + c] = acc[k];
+  }
+}
+
+// grad_w[c * 25 + tap] = sum over CTAs (warp per output, fixed order) of partial[cta][tap][c]
+__global__ void wgrad_edge_finalize_kernel(const float* __restrict__ partial, int n_partials, int C,
+                                           float* __restrict__ grad_w) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (o >= 25 * C) return;
+  const double s = warp_sum_partials(partial + o, n_partials, static_cast<size_t>(25) * C, lane);
+  if (lane == 0) grad_w[(o % C) * 25 + o / C] = static_cast<float>(s);
+}
+
 // sum the split partials (fixed order) and scatter to the torch layout
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int cin, int cout,
                                       int transposed, float* __restrict__ grad_w) {
@@ -423,10 +661,13 @@ struct TrainWs {
   float* dz6;                 // [B][512][128]
   float* w_fwd[12]; float* w_t[12];
   float* mean[12]; float* invstd[12]; float* sum_g[12]; float* sum_gx[12];
-  float* red_partial;         // [kRedSplits][2][512]
+  float* red_partial;         // [kRedBlocksMax][2][512]
   float* wgrad_partial;
   size_t wgrad_partial_floats;
   float* scalar_partial;      // [1024 * 2]
+  float* zero_bias;           // [512] zeros (data-gradient convolutions have no bias)
+  float* splitk;              // split-K scratch of the tcgen05 conv kernels (non-cluster fallback)
+  size_t splitk_bytes;
   size_t total;
 };
 
@@ -460,34 +701,68 @@ static int wgrad_splits(int li, int batch) {
   return s;
 }
 
+// the S / L operands of layer li's weight gradient (see wgrad_tc.cu) in the training workspace layout
+struct WgOperands { int gh, gw, s_c, l_c, s_pitch, l_pitch, s_coff, l_coff; };
+static WgOperands wg_operands(int li) {
+  const LayerGeom& g = kLayers[li];
+  WgOperands o{};
+  if (!g.transposed) {          // conv: S = dz (cout), L = x (cin)
+    o.gh = g.hout; o.gw = g.wout; o.s_c = g.cout; o.s_pitch = g.cout; o.s_coff = 0;
+    o.l_c = g.cin; o.l_pitch = g.in_buf >= 0 ? kBufGeom[g.in_buf].c : 1; o.l_coff = g.in_coff;
+  } else {                      // deconv: S = x (cin), L = dz (cout)
+    o.gh = g.hin; o.gw = g.win; o.s_c = g.cin; o.s_pitch = kBufGeom[g.in_buf].c; o.s_coff = g.in_coff;
+    o.l_c = g.cout; o.l_pitch = g.cout; o.l_coff = 0;
+  }
+  return o;
+}
+static bool wgrad_on_tc(int li) {
+  if (li < 1 || li > 10) return false;
+  const WgOperands o = wg_operands(li);
+  return wgrad_tc_supported(o.gh, o.gw, o.s_c, o.l_c, o.s_pitch, o.l_pitch, o.s_coff, o.l_coff);
+}
+
 static TrainWs carve_train(char* base, int batch) {
   TrainWs w{};
   size_t off = 0;
   auto take = [&](size_t floats) {
     float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
-    off += (floats * sizeof(float) + 255) / 256 * 256;
+    off += (floats * sizeof(float) + 1023) / 1024 * 1024;     // 1024-byte aligned: TMA bases, 16-byte row accesses
     return p;
   };
   for (int i = 0; i < BUF_COUNT; ++i) {
-    const size_t n = static_cast<size_t>(batch) * kBufGeom[i].h * kBufGeom[i].w * kBufGeom[i].c;
+    // batch padded like the inference workspace: the deep-layer M tiles span 8 patches
+    const size_t n = static_cast<size_t>(padded_batch(batch)) * kBufGeom[i].h * kBufGeom[i].w * kBufGeom[i].c;
     w.cat[i] = take(n);
     w.dcat[i] = take(n);
   }
   size_t wg = 0;
   for (int li = 0; li < 12; ++li) {
     const LayerGeom& g = kLayers[li];
-    w.z[li] = li < 11 ? take(static_cast<size_t>(batch) * g.hout * g.wout * g.cout) : nullptr;
+    w.z[li] = li < 11 ? take(static_cast<size_t>(padded_batch(batch)) * g.hout * g.wout * g.cout) : nullptr;
     w.w_fwd[li] = take(static_cast<size_t>(25) * g.cin * g.cout);
     w.w_t[li] = take(static_cast<size_t>(25) * g.cin * g.cout);
     w.mean[li] = take(g.cout); w.invstd[li] = take(g.cout); w.sum_g[li] = take(g.cout); w.sum_gx[li] = take(g.cout);
-    const size_t need = static_cast<size_t>(wgrad_splits(li, batch)) * 25 * g.cin * g.cout;
+    size_t need = static_cast<size_t>(wgrad_splits(li, batch)) * 25 * g.cin * g.cout;
+    if (wgrad_on_tc(li)) {
+      const WgOperands o = wg_operands(li);
+      const size_t tc = wgrad_tc_partial_floats(o.gh, o.gw, batch, o.s_c, o.l_c);
+      need = tc > need ? tc : need;
+    }
     wg = need > wg ? need : wg;
   }
+  {
+    const size_t edge = static_cast<size_t>(batch) * (256 / kEdgeRows) * 25 * 32;     // wgrad_edge_kernel partials
+    wg = edge > wg ? edge : wg;
+  }
   w.dz6 = take(static_cast<size_t>(batch) * 512 * 128);
-  w.red_partial = take(static_cast<size_t>(kRedSplits) * 2 * 512);
+  w.red_partial = take(static_cast<size_t>(kRedBlocksMax) * 2 * 512);
   w.wgrad_partial = take(wg);
   w.wgrad_partial_floats = wg;
   w.scalar_partial = take(2048);
+  w.zero_bias = take(512);
+  // split-K scratch: upper bound over the forward / dgrad problems (M tiles x 128 x Cout x split <= 8)
+  w.splitk_bytes = static_cast<size_t>(64) << 20;
+  w.splitk = take(w.splitk_bytes / sizeof(float));
   w.total = off;
   return w;
 }
@@ -497,9 +772,73 @@ static unsigned grid_for(size_t n) {
   return static_cast<unsigned>(b > 148 * 32 ? 148 * 32 : (b ? b : 1));
 }
 
+// data-gradient problem of layer li: conv -> transposed conv (Cout -> Cin) and vice versa, on dz (dense, pitch Cout)
+// writing into the gradient concat buffer of the layer's input
+static ConvDesc dgrad_desc(int li) {
+  const LayerGeom& g = kLayers[li];
+  ConvDesc d;
+  d.transposed = !g.transposed;
+  d.cin = g.cout; d.cout = g.cin;
+  d.hin = g.hout; d.win = g.wout; d.hout = g.hin; d.wout = g.win;
+  d.in_pitch = g.cout; d.in_coff = 0;
+  d.out_pitch = kBufGeom[g.in_buf].c; d.out_coff = g.in_coff;
+  d.act = ACT_NONE;
+  return d;
+}
+// train-mode forward problem of layer li: raw convolution + bias into the dense pre-BatchNorm buffer z
+static ConvDesc train_fwd_desc(int li) {
+  ConvDesc d = desc_of_layer(li);
+  d.out_pitch = d.cout; d.out_coff = 0;
+  d.act = ACT_NONE;
+  return d;
+}
+
 }  // namespace svs
 
+struct svs_train_plan {
+  int device = 0;
+  svs::TcLayer fwd[12];       // layers 1..10
+  svs::TcLayer dgr[12];       // layers 1..10
+  void* d6_weights = nullptr; // deconv6 as taps-as-N GEMM (deconv6_tc.cu), TF32
+  CUtensorMap d6_tmap;
+};
+
 using namespace svs;
+
+extern "C" int svs_unet_train_plan_create(void* stream, svs_train_plan** plan_out) {
+  SVS_REQUIRE(plan_out, "svs_unet_train_plan_create: null pointer");
+  int dev = 0;
+  SVS_CUDA_TRY(cudaGetDevice(&dev));
+  int rc = svs_device_check(dev);
+  if (rc != SVS_OK) return rc;
+  svs_train_plan* plan = new (std::nothrow) svs_train_plan();
+  if (!plan) return fail(SVS_ERR_CUDA, "svs_unet_train_plan_create: out of host memory");
+  plan->device = dev;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int li = 1; li <= 10; ++li) {
+    rc = tc_plan_one(plan->fwd[li], train_fwd_desc(li), nullptr, true, st);
+    if (rc == SVS_OK) rc = tc_plan_one(plan->dgr[li], dgrad_desc(li), nullptr, true, st);
+    if (rc == SVS_OK && !(plan->fwd[li].enabled && plan->dgr[li].enabled))
+      rc = fail(SVS_ERR_NOT_IMPLEMENTED, "svs_unet_train_plan_create: no tcgen05 mapping for layer " + std::to_string(li));
+    if (rc != SVS_OK) { svs_unet_train_plan_destroy(plan); return rc; }
+  }
+  if (cudaMalloc(&plan->d6_weights, 32 * 32 * sizeof(float)) != cudaSuccess) {
+    svs_unet_train_plan_destroy(plan);
+    return fail(SVS_ERR_CUDA, "svs_unet_train_plan_create: cudaMalloc failed");
+  }
+  rc = d6_make_weight_map(plan->d6_weights, true, &plan->d6_tmap);
+  if (rc != SVS_OK) { svs_unet_train_plan_destroy(plan); return rc; }
+  *plan_out = plan;
+  return SVS_OK;
+}
+
+extern "C" int svs_unet_train_plan_destroy(svs_train_plan* plan) {
+  if (!plan) return SVS_OK;
+  for (int li = 0; li < 12; ++li) { tc_free_one(plan->fwd[li]); tc_free_one(plan->dgr[li]); }
+  if (plan->d6_weights) cudaFree(plan->d6_weights);
+  delete plan;
+  return SVS_OK;
+}
 
 extern "C" size_t svs_unet_train_workspace_bytes(int batch) {
   if (batch <= 0) return 0;
@@ -510,7 +849,7 @@ static int check_train_args(const svs_train_layer layers[12], const void* mix, i
                             size_t workspace_bytes) {
   SVS_REQUIRE(layers && mix && workspace, "svs_unet_train: null pointer");
   SVS_REQUIRE(batch >= 1, "svs_unet_train: batch must be positive");   // B = 1 is fine: N = B*H*W >= 16 per channel
-  SVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "svs_unet_train: workspace must be 256-byte aligned");
+  SVS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "svs_unet_train: workspace must be 1024-byte aligned");
   for (int i = 0; i < 12; ++i) {
     SVS_REQUIRE(layers[i].weight && layers[i].bias, "svs_unet_train: weight/bias missing");
     SVS_REQUIRE((layers[i].bn_weight != nullptr) == (i != 11), "svs_unet_train: BatchNorm on every block but deconv6");
@@ -520,8 +859,33 @@ static int check_train_args(const svs_train_layer layers[12], const void* mix, i
   return SVS_OK;
 }
 
-extern "C" int svs_unet_train_forward(const svs_train_layer layers[12], const float* mix, int batch,
-                                      int update_running_stats, float* mask_out, void* workspace,
+namespace svs {
+// per-channel two-stage reduction of layer li (mode 0: BatchNorm statistics, mode 1: BatchNorm backward sums);
+// returns the number of stage-1 partials through *splits
+template <int kMode>
+static int run_channel_reduce(const RedArgs& a, float* partial, int* splits, bool fast, cudaStream_t st) {
+  const int pix_log2 = ilog2_exact(a.pix_per_sample);
+  if (fast && a.C % 4 == 0 && a.C <= 1024 && 256 % (a.C / 4) == 0 && a.y_pitch % 4 == 0 && a.y_coff % 4 == 0 &&
+      (kMode == 0 || pix_log2 >= 0)) {
+    const int rows = 256 / (a.C / 4);
+    size_t blocks = (a.N + static_cast<size_t>(rows) * 8 - 1) / (static_cast<size_t>(rows) * 8);   // >= 8 iterations per CTA
+    if (blocks > static_cast<size_t>(kRedBlocksMax)) blocks = kRedBlocksMax;
+    if (blocks < 1) blocks = 1;
+    channel_reduce_rows_kernel<kMode><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, pix_log2 < 0 ? 0 : pix_log2, partial);
+    SVS_CHECK_LAUNCH("channel_reduce_rows_kernel");
+    *splits = static_cast<int>(blocks);
+    return SVS_OK;
+  }
+  dim3 rgrid((a.C + 31) / 32, kRedSplits);
+  channel_reduce_kernel<kMode><<<rgrid, 256, 0, st>>>(a, partial);
+  SVS_CHECK_LAUNCH("channel_reduce_kernel");
+  *splits = kRedSplits;
+  return SVS_OK;
+}
+}  // namespace svs
+
+extern "C" int svs_unet_train_forward(const svs_train_plan* plan, const svs_train_layer layers[12], const float* mix,
+                                      int batch, int update_running_stats, float* mask_out, void* workspace,
                                       size_t workspace_bytes, void* stream) {
   int rc = check_train_args(layers, mix, batch, workspace, workspace_bytes);
   if (rc != SVS_OK) return rc;
@@ -532,6 +896,8 @@ extern "C" int svs_unet_train_forward(const svs_train_layer layers[12], const fl
   if (rc != SVS_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TrainWs w = carve_train(static_cast<char*>(workspace), batch);
+  const bool tc = plan != nullptr;
+  if (tc) SVS_CUDA_TRY(cudaMemsetAsync(w.zero_bias, 0, 512 * sizeof(float), st));
   for (int li = 0; li < 12; ++li) {
     const LayerGeom& g = kLayers[li];
     const svs_train_layer& L = layers[li];
@@ -539,28 +905,60 @@ extern "C" int svs_unet_train_forward(const svs_train_layer layers[12], const fl
                                                                     w.w_fwd[li], w.w_t[li]);
     SVS_CHECK_LAUNCH("train_pack_kernel");
     if (li == 11) {                                                // deconv6 + sigmoid -> mask
-      rc = launch_deconv6_f32(w.cat[BUF_CAT1], w.w_fwd[11], L.bias, mask_out, batch, st);
+      if (tc) {
+        rc = d6_pack(w.w_fwd[11], true, plan->d6_weights, st);
+        if (rc != SVS_OK) return rc;
+        svs_patch_view iv{const_cast<float*>(mix), nullptr, 512 * 128, 128, 1};
+        svs_patch_view ov{mask_out, nullptr, 512 * 128, 128, 1};
+        rc = d6_launch_raw(true, plan->d6_tmap, L.bias, w.cat[BUF_CAT1], &iv, &ov, nullptr, batch, 0, st);
+      } else {
+        rc = launch_deconv6_f32(w.cat[BUF_CAT1], w.w_fwd[11], L.bias, mask_out, batch, st);
+      }
       if (rc != SVS_OK) return rc;
+      // the backward needs the mask (sigmoid') and gets only the workspace: keep a copy
+      SVS_CUDA_TRY(cudaMemcpyAsync(w.dz6, mask_out, sizeof(float) * static_cast<size_t>(batch) * 512 * 128,
+                                   cudaMemcpyDeviceToDevice, st));
       break;
     }
-    if (li == 0) rc = launch_conv1_f32(mix, w.w_fwd[0], L.bias, w.z[0], batch, st);
-    else rc = launch_conv_direct_f32(w.cat[g.in_buf], kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win, g.cin,
-                                     w.w_fwd[li], L.bias, w.z[li], g.cout, 0, g.hout, g.wout, g.cout, ACT_NONE,
-                                     g.transposed, batch, false, st);
+    if (li == 0) {
+      rc = launch_conv1_f32(mix, w.w_fwd[0], L.bias, w.z[0], batch, st);
+    } else if (tc) {
+      TcLayer& t = const_cast<TcLayer&>(plan->fwd[li]);            // the plan owns only packed weights: rewritten per step
+      rc = tc_pack_one(t, w.w_fwd[li], true, st);
+      if (rc != SVS_OK) return rc;
+      TcIo io;
+      io.in = w.cat[g.in_buf]; io.out = w.z[li]; io.bias = L.bias;
+      io.splitk = w.splitk; io.splitk_bytes = w.splitk_bytes;
+      io.out_flags = OUT_KEEP_FP32;
+      rc = tc_launch(t, io, batch, true, st);
+    } else {
+      rc = launch_conv_direct_f32(w.cat[g.in_buf], kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win, g.cin,
+                                  w.w_fwd[li], L.bias, w.z[li], g.cout, 0, g.hout, g.wout, g.cout, ACT_NONE,
+                                  g.transposed, batch, false, st);
+    }
     if (rc != SVS_OK) return rc;
     const size_t N = static_cast<size_t>(batch) * g.hout * g.wout;
     RedArgs a{};
-    a.z = w.z[li]; a.C = g.cout; a.N = N;
-    dim3 rgrid((g.cout + 31) / 32, kRedSplits);
-    channel_reduce_kernel<0><<<rgrid, 256, 0, st>>>(a, w.red_partial);
-    SVS_CHECK_LAUNCH("channel_reduce_kernel<0>");
-    bn_finalize_kernel<<<(g.cout + 127) / 128, 128, 0, st>>>(w.red_partial, kRedSplits, g.cout, static_cast<double>(N),
+    a.z = w.z[li]; a.C = g.cout; a.N = N; a.pix_per_sample = g.hout * g.wout;
+    int splits = 0;
+    rc = run_channel_reduce<0>(a, w.red_partial, &splits, true, st);
+    if (rc != SVS_OK) return rc;
+    bn_finalize_kernel<<<(g.cout + 3) / 4, 128, 0, st>>>(w.red_partial, splits, g.cout, static_cast<double>(N),
                                                             w.mean[li], w.invstd[li], L.bn_running_mean,
                                                             L.bn_running_var, update_running_stats);
     SVS_CHECK_LAUNCH("bn_finalize_kernel");
-    bn_apply_kernel<<<grid_for(N * g.cout), 256, 0, st>>>(w.z[li], N, g.cout, w.mean[li], w.invstd[li], L.bn_weight,
-                                                         L.bn_bias, L.dropout_keep, g.hout * g.wout, g.act,
-                                                         w.cat[g.out_buf], kBufGeom[g.out_buf].c, g.out_coff);
+    {
+      const int cg_log2 = ilog2_exact(g.cout / 4), pix_log2 = ilog2_exact(g.hout * g.wout);
+      if (cg_log2 >= 0 && pix_log2 >= 0)
+        bn_apply_vec_kernel<<<grid_for(N * g.cout / 4), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(w.z[li]), N * (g.cout / 4), cg_log2, w.mean[li], w.invstd[li], L.bn_weight,
+            L.bn_bias, L.dropout_keep, pix_log2, g.act, w.cat[g.out_buf], kBufGeom[g.out_buf].c, g.out_coff, tc ? 1 : 0);
+      else
+        bn_apply_kernel<<<grid_for(N * g.cout), 256, 0, st>>>(w.z[li], N, g.cout, w.mean[li], w.invstd[li], L.bn_weight,
+                                                             L.bn_bias, L.dropout_keep, g.hout * g.wout, g.act,
+                                                             w.cat[g.out_buf], kBufGeom[g.out_buf].c, g.out_coff,
+                                                             tc ? 1 : 0);
+    }
     SVS_CHECK_LAUNCH("bn_apply_kernel");
   }
   return SVS_OK;
@@ -568,8 +966,30 @@ extern "C" int svs_unet_train_forward(const svs_train_layer layers[12], const fl
 
 namespace svs {
 static int run_wgrad(const TrainWs& w, const svs_train_layer& L, int li, int batch, const float* dY, int dy_pitch,
-                     int dy_coff, const float* X, int x_pitch, int x_coff, cudaStream_t st) {
+                     int dy_coff, const float* X, int x_pitch, int x_coff, bool tc, cudaStream_t st) {
   const LayerGeom& g = kLayers[li];
+  if (li == 0 || li == 11) {       // single-channel edge layers: one streaming pass (both arithmetic modes)
+    const float* S = li == 0 ? dY : X;
+    const float* Lt = li == 0 ? X : dY;
+    dim3 grid(256 / kEdgeRows, batch);
+    const int n_partials = static_cast<int>(grid.x * grid.y);
+    const int C = li == 0 ? 16 : 32;
+    if (w.wgrad_partial_floats < static_cast<size_t>(n_partials) * 25 * C)
+      return fail(SVS_ERR_WORKSPACE, "run_wgrad: partial buffer too small");
+    if (li == 0) wgrad_edge_kernel<16><<<grid, 256, 0, st>>>(S, Lt, w.wgrad_partial);
+    else wgrad_edge_kernel<32><<<grid, 256, 0, st>>>(S, Lt, w.wgrad_partial);
+    SVS_CHECK_LAUNCH("wgrad_edge_kernel");
+    wgrad_edge_finalize_kernel<<<(25 * C * 32 + 127) / 128, 128, 0, st>>>(w.wgrad_partial, n_partials, C, L.grad_weight);
+    SVS_CHECK_LAUNCH("wgrad_edge_finalize_kernel");
+    return SVS_OK;
+  }
+  if (tc && wgrad_on_tc(li)) {
+    const WgOperands o = wg_operands(li);
+    const float* S = g.transposed ? X : dY;
+    const float* Lt = g.transposed ? dY : X;
+    return wgrad_tc_launch(S, o.s_pitch, o.s_coff, o.s_c, Lt, o.l_pitch, o.l_coff, o.l_c, o.gh, o.gw, batch,
+                           w.wgrad_partial, w.wgrad_partial_floats, L.grad_weight, st);
+  }
   WgradArgs a{};
   a.cin = g.cin; a.cout = g.cout; a.batch = batch;
   if (!g.transposed) {             // conv: small grid = output (dY), large = input (X)
@@ -599,8 +1019,9 @@ static int run_wgrad(const TrainWs& w, const svs_train_layer& L, int li, int bat
 }
 }  // namespace svs
 
-extern "C" int svs_unet_train_backward(const svs_train_layer layers[12], const float* mix, const float* grad_mask,
-                                       int batch, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int svs_unet_train_backward(const svs_train_plan* plan, const svs_train_layer layers[12], const float* mix,
+                                       const float* grad_mask, int batch, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
   int rc = check_train_args(layers, mix, batch, workspace, workspace_bytes);
   if (rc != SVS_OK) return rc;
   SVS_REQUIRE(grad_mask, "svs_unet_train_backward: null grad_mask");
@@ -610,21 +1031,18 @@ extern "C" int svs_unet_train_backward(const svs_train_layer layers[12], const f
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TrainWs w = carve_train(static_cast<char*>(workspace), batch);
+  const bool tc = plan != nullptr;
   // ---- deconv6: sigmoid backward, bias / weight gradient, data gradient into dcat1 (all 32 channels) ----
-  // the mask is recomputed from the forward's output held by the caller? No: m(1-m) needs the mask; the
-  // forward wrote it to mask_out only, so dz6 is formed from grad_mask and the mask re-derived here.
+  // dz6 holds the forward's mask; dz6 <- grad * m (1 - m) in place
   {
     const size_t n = static_cast<size_t>(batch) * 512 * 128;
-    // recompute the mask into dz6 (deterministic: same kernel, same inputs), then dz6 <- grad * m (1 - m)
-    rc = launch_deconv6_f32(w.cat[BUF_CAT1], w.w_fwd[11], layers[11].bias, w.dz6, batch, st);
-    if (rc != SVS_OK) return rc;
     sigmoid_bwd_kernel<<<grid_for(n), 256, 0, st>>>(w.dz6, grad_mask, n, w.dz6);
     SVS_CHECK_LAUNCH("sigmoid_bwd_kernel");
     sum_stage1_kernel<<<1024, 256, 0, st>>>(w.dz6, n, w.scalar_partial);
     SVS_CHECK_LAUNCH("sum_stage1_kernel");
     sum_stage2_kernel<<<1, 1, 0, st>>>(w.scalar_partial, 1024, 1.0f, layers[11].grad_bias);
     SVS_CHECK_LAUNCH("sum_stage2_kernel");
-    rc = run_wgrad(w, layers[11], 11, batch, w.dz6, 1, 0, w.cat[BUF_CAT1], 32, 0, st);
+    rc = run_wgrad(w, layers[11], 11, batch, w.dz6, 1, 0, w.cat[BUF_CAT1], 32, 0, tc, st);
     if (rc != SVS_OK) return rc;
     const size_t threads = static_cast<size_t>(batch) * 256 * 64 * 8;
     deconv6_dgrad_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(w.dz6, w.w_fwd[11],
@@ -642,28 +1060,48 @@ extern "C" int svs_unet_train_backward(const svs_train_layer layers[12], const f
     a.y_pitch = kBufGeom[g.out_buf].c; a.y_coff = g.out_coff;
     a.keep = L.dropout_keep; a.mean = w.mean[li]; a.invstd = w.invstd[li];
     a.act = g.act; a.pix_per_sample = g.hout * g.wout;
-    dim3 rgrid((g.cout + 31) / 32, kRedSplits);
-    channel_reduce_kernel<1><<<rgrid, 256, 0, st>>>(a, w.red_partial);
-    SVS_CHECK_LAUNCH("channel_reduce_kernel<1>");
-    bn_bwd_finalize_kernel<<<(g.cout + 127) / 128, 128, 0, st>>>(w.red_partial, kRedSplits, g.cout, w.sum_g[li],
+    int splits = 0;
+    rc = run_channel_reduce<1>(a, w.red_partial, &splits, true, st);
+    if (rc != SVS_OK) return rc;
+    bn_bwd_finalize_kernel<<<(g.cout + 3) / 4, 128, 0, st>>>(w.red_partial, splits, g.cout, w.sum_g[li],
                                                                 w.sum_gx[li], L.grad_bn_weight, L.grad_bn_bias,
                                                                 L.grad_bias);
     SVS_CHECK_LAUNCH("bn_bwd_finalize_kernel");
-    bn_bwd_apply_kernel<<<grid_for(N * g.cout), 256, 0, st>>>(a, L.bn_weight, w.sum_g[li], w.sum_gx[li], w.z[li]);
+    {
+      const int cg_log2 = ilog2_exact(g.cout / 4), pix_log2 = ilog2_exact(g.hout * g.wout);
+      if (cg_log2 >= 0 && pix_log2 >= 0)
+        bn_bwd_apply_vec_kernel<<<grid_for(N * g.cout / 4), 256, 0, st>>>(a, cg_log2, pix_log2, L.bn_weight, w.sum_g[li],
+                                                                         w.sum_gx[li], reinterpret_cast<float4*>(w.z[li]),
+                                                                         tc ? 1 : 0);
+      else
+        bn_bwd_apply_kernel<<<grid_for(N * g.cout), 256, 0, st>>>(a, L.bn_weight, w.sum_g[li], w.sum_gx[li], w.z[li],
+                                                                 tc ? 1 : 0);
+    }
     SVS_CHECK_LAUNCH("bn_bwd_apply_kernel");
     // now z[li] holds dz (gradient w.r.t. the conv output)
     const float* X = li == 0 ? mix : w.cat[g.in_buf];
     const int x_pitch = li == 0 ? 1 : kBufGeom[g.in_buf].c;
-    rc = run_wgrad(w, L, li, batch, w.z[li], g.cout, 0, X, x_pitch, g.in_coff, st);
+    rc = run_wgrad(w, L, li, batch, w.z[li], g.cout, 0, X, x_pitch, g.in_coff, tc, st);
     if (rc != SVS_OK) return rc;
     if (li == 0) break;                                            // the mixture needs no gradient
     // data gradient into dcat[in_buf][in_coff .. in_coff + cin): conv dgrad = transposed kernel, deconv dgrad =
     // conv kernel, both with channel-transposed weights.  Encoder layers ACCUMULATE into the skip half that the
     // decoder consumer has already written (decoder layers run first in this loop).
     const bool accumulate = !g.transposed;
-    rc = launch_conv_direct_f32(w.z[li], g.cout, 0, g.hout, g.wout, g.cout, w.w_t[li], nullptr, w.dcat[g.in_buf],
-                                kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win, g.cin, ACT_NONE, !g.transposed, batch,
-                                accumulate, st);
+    if (tc) {
+      TcLayer& t = const_cast<TcLayer&>(plan->dgr[li]);
+      rc = tc_pack_one(t, w.w_t[li], true, st);
+      if (rc != SVS_OK) return rc;
+      TcIo io;
+      io.in = w.z[li]; io.out = w.dcat[g.in_buf]; io.bias = w.zero_bias;
+      io.splitk = w.splitk; io.splitk_bytes = w.splitk_bytes;
+      io.out_flags = OUT_KEEP_FP32 | (accumulate ? OUT_ACCUMULATE : 0);
+      rc = tc_launch(t, io, batch, true, st);
+    } else {
+      rc = launch_conv_direct_f32(w.z[li], g.cout, 0, g.hout, g.wout, g.cout, w.w_t[li], nullptr, w.dcat[g.in_buf],
+                                  kBufGeom[g.in_buf].c, g.in_coff, g.hin, g.win, g.cin, ACT_NONE, !g.transposed, batch,
+                                  accumulate, st);
+    }
     if (rc != SVS_OK) return rc;
   }
   return SVS_OK;

@@ -43,6 +43,39 @@ static const LayerGeom kLayers[12] = {
     {true, 32, 1, 256, 64, 512, 128, BUF_CAT1, 0, -1, 0, ACT_NONE},
 };
 
+// One convolution / transposed-convolution PROBLEM on NHWC buffers: an inference layer (desc_of_layer) or a pass of
+// the training step (train-mode forward, data gradient).  The tcgen05 planners below take this, not a layer index.
+struct ConvDesc {
+  bool transposed = false;
+  int cin = 0, cout = 0;
+  int hin = 0, win = 0, hout = 0, wout = 0;
+  int in_pitch = 0, in_coff = 0;     // channels per pixel of the input buffer / first channel read
+  int out_pitch = 0, out_coff = 0;   // channels per pixel of the output buffer / first channel written
+  int act = ACT_NONE;
+};
+inline ConvDesc desc_of_layer(int li) {
+  const LayerGeom& g = kLayers[li];
+  ConvDesc d;
+  d.transposed = g.transposed; d.cin = g.cin; d.cout = g.cout;
+  d.hin = g.hin; d.win = g.win; d.hout = g.hout; d.wout = g.wout;
+  d.in_pitch = g.in_buf >= 0 ? kBufGeom[g.in_buf].c : 1; d.in_coff = g.in_coff;
+  d.out_pitch = g.out_buf >= 0 ? kBufGeom[g.out_buf].c : 1; d.out_coff = g.out_coff;
+  d.act = g.act;
+  return d;
+}
+// epilogue modifiers of the tcgen05 conv kernels
+enum OutFlags { OUT_ACCUMULATE = 1,   // out += result (data gradients meeting at a skip connection)
+                OUT_KEEP_FP32 = 2 };  // fp32 outputs are NOT rounded to TF32 (pre-BatchNorm z, gradients)
+struct TcIo {                         // buffers of one launch
+  const void* in = nullptr;
+  void* out = nullptr;
+  const float* bias = nullptr;
+  float* splitk = nullptr;
+  size_t splitk_bytes = 0;
+  int out_flags = 0;
+  long long* dbg = nullptr;
+};
+
 constexpr int kBatchPad = 8;      // workspace batch is padded to a multiple of 8 (deep-layer M tiles)
 inline int padded_batch(int b) { return (b + kBatchPad - 1) / kBatchPad * kBatchPad; }
 
@@ -73,6 +106,8 @@ struct TcPhase {
 struct TcLayer {
   bool enabled = false;
   int layer = -1;
+  ConvDesc d;                        // the problem this plan was made for
+  int2* d_src = nullptr;             // device: (tap, first channel) of every K chunk (kept for re-packing)
   int bw = 0, bh = 0, nb = 0;        // M tile = bw x bh x nb = 128 pixels
   int gw = 0, gh = 0;                // pixel grid the M index runs over (conv: output, deconv: input)
   int block_n = 0;                   // N tile

@@ -10,11 +10,14 @@
 There is no CPU path."""
 from __future__ import annotations
 
+import os
 from ctypes import byref
 
 import torch
 
 from . import _lib
+
+TRAIN_PRECISION = "tf32"       # default arithmetic of the training step (see train_precision)
 
 _LAYERS = ["conv1", "conv2", "conv3", "conv4", "conv5", "conv6",
            "deconv1", "deconv2", "deconv3", "deconv4", "deconv5", "deconv6"]
@@ -44,14 +47,40 @@ def param_list(model):
 
 
 def _workspace(model, batch):
-    ws = getattr(model, "_train_ws", None)
-    if ws is None or ws[0] != batch:
+    """Per-model training workspace (saved activations, gradients, scratch) for `batch` patches; the two most recent
+    batch sizes are kept (a captured step graph is tied to its workspace address)."""
+    cache = model.__dict__.setdefault("_train_ws", {})
+    ws = cache.get(batch)
+    if ws is None:
         nbytes = _lib.load().svs_unet_train_workspace_bytes(batch)
         dev = next(model.parameters()).device
-        raw = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
-        off = (-raw.data_ptr()) % 256
-        model._train_ws = (batch, raw[off:off + nbytes])
-    return model._train_ws[1]
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        off = (-raw.data_ptr()) % 1024
+        ws = raw[off:off + nbytes]
+        if len(cache) >= 2:
+            cache.pop(next(iter(cache)))
+        cache[batch] = ws
+    return ws
+
+
+def train_precision(model) -> str:
+    """"tf32" (default: tcgen05 kind::tf32 for forward / dgrad / wgrad, what torch + cuDNN do for the reference's fp32
+    model on a GPU) or "fp32" (exact CUDA-core arithmetic).  Set ``model.train_precision`` or SVS_B200_TRAIN_PRECISION."""
+    p = getattr(model, "train_precision", None) or os.environ.get("SVS_B200_TRAIN_PRECISION", TRAIN_PRECISION)
+    if p not in ("tf32", "fp32"):
+        raise _lib.SvsError(f"train precision must be 'tf32' or 'fp32', got {p!r}")
+    return p
+
+
+def _plan_handle(model):
+    if train_precision(model) == "fp32":
+        return None
+    dev = next(model.parameters()).device
+    plan = getattr(model, "_train_plan", None)
+    if plan is None or plan.device != dev:
+        plan = _lib.TrainPlan(dev)
+        model._train_plan = plan
+    return plan.handle
 
 
 def _flat_grads(model):
@@ -133,13 +162,12 @@ def _raw_forward(model, mix, masks, update_running=True):
     # differentiating the wrong graph
     model._train_gen = getattr(model, "_train_gen", 0) + 1
     with torch.cuda.device(mix.device):
-        _lib.check(_lib.load().svs_unet_train_forward(arr, mix.data_ptr(), b, 1 if update_running else 0,
+        _lib.check(_lib.load().svs_unet_train_forward(_plan_handle(model), arr, mix.data_ptr(), b,
+                                                      1 if update_running else 0,
                                                       mask.data_ptr(), ws.data_ptr(), ws.numel(),
                                                       _lib.stream_ptr(mix.device)), "svs_unet_train_forward")
     if update_running:
-        for i in range(11):
-            _, bn, _ = _layer_modules(model, i)
-            bn.num_batches_tracked += 1
+        torch._foreach_add_([_layer_modules(model, i)[1].num_batches_tracked for i in range(11)], 1)
     return mask
 
 
@@ -148,7 +176,8 @@ def _raw_backward(model, mix, grad_mask, masks, grads):
     ws = _workspace(model, b)
     arr = _layer_structs(model, grads, masks, need_grads=True)
     with torch.cuda.device(mix.device):
-        _lib.check(_lib.load().svs_unet_train_backward(arr, mix.data_ptr(), grad_mask.data_ptr(), b, ws.data_ptr(),
+        _lib.check(_lib.load().svs_unet_train_backward(_plan_handle(model), arr, mix.data_ptr(), grad_mask.data_ptr(), b,
+                                                       ws.data_ptr(),
                                                        ws.numel(), _lib.stream_ptr(mix.device)),
                    "svs_unet_train_backward")
 
@@ -202,31 +231,112 @@ def masked_l1(mask, mix, voc, two_term=True, grad_scale=1.0, want_grad=True):
     return loss, grad
 
 
-TRAIN_PRECISION = "fp32"
+
+
+def _step_body(model, mix, voc, two_term, loss_scale, injected_masks):
+    """forward -> fused loss + dL/dmask -> backward into the flat gradient buffer (all on the current stream)."""
+    masks = dropout_masks(model, mix.shape[0], injected_masks)
+    flat, views = _flat_grads(model)
+    mask = _raw_forward(model, mix, masks)
+    loss, grad_mask = masked_l1(mask, mix, voc, two_term, loss_scale)
+    _raw_backward(model, mix, grad_mask, masks, views)
+    return loss
+
+
+class _StepGraph:
+    """One CUDA graph of ``_step_body`` for a fixed batch size: the step is ~250 small launches (pack, conv, BatchNorm
+    reduce / finalize / apply, dgrad, wgrad per layer), i.e. launch-bound when issued one by one from Python."""
+
+    def __init__(self, model, mix, voc, two_term, loss_scale):
+        dev = mix.device
+        self.mix = torch.empty_like(mix)
+        self.voc = torch.empty_like(voc)
+        self.mix.copy_(mix)
+        self.voc.copy_(voc)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                                 # warm-up outside capture: lazy initialisation,
+            for _ in range(2):                                        # workspace / flat-buffer allocation
+                _step_body(model, self.mix, self.voc, two_term, loss_scale, None)
+            # the warm-up steps must not count: restore the BatchNorm buffers they advanced
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = _step_body(model, self.mix, self.voc, two_term, loss_scale, None)
+
+    def run(self, mix, voc):
+        self.mix.copy_(mix)
+        self.voc.copy_(voc)
+        self.graph.replay()
+        return self.loss
+
+
+def _bn_buffers(model):
+    out = []
+    for i in range(11):
+        _, bn, _ = _layer_modules(model, i)
+        out += [bn.running_mean, bn.running_var, bn.num_batches_tracked]
+    return out
+
+
+def _graph_step(model, mix, voc, two_term, loss_scale):
+    key = (mix.shape[0], bool(two_term), float(loss_scale), train_precision(model), str(mix.device),
+           tuple(float(_layer_modules(model, i)[2].p) for i in range(6, 11)),
+           tuple(p.data_ptr() for p in param_list(model)), _workspace(model, mix.shape[0]).data_ptr())
+    cache = model.__dict__.setdefault("_step_graphs", {})
+    g = cache.get(key)
+    if g is None:
+        saved = [b.clone() for b in _bn_buffers(model)]               # capture + warm-up run real steps on the buffers
+        if len(cache) >= 2:
+            cache.pop(next(iter(cache)))
+        g = _StepGraph(model, mix, voc, two_term, loss_scale)
+        for b, v in zip(_bn_buffers(model), saved):
+            b.copy_(v)
+        cache[key] = g
+        model._train_gen = getattr(model, "_train_gen", 0) + 1
+    return g.run(mix, voc)
+
+
+def _sync_grads(model, flat):
+    """Data parallel: average the flat gradient buffer across ranks.  The buffer is cut into buckets that are
+    all-reduced back to back on NCCL's stream (no bucket waits for the host)."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return
+    world = torch.distributed.get_world_size()
+    if world <= 1:
+        return
+    n = flat.numel()
+    bucket = 1 << 22                                                  # 16 MB of fp32 per bucket
+    works = []
+    for a in range(0, n, bucket):
+        works.append(torch.distributed.all_reduce(flat[a:min(n, a + bucket)], async_op=True))
+    for w in works:
+        w.wait()
+    flat.div_(world)
 
 
 def train_step(model, mix, voc, two_term: bool = True, loss_scale: float = 1.0, step: bool = True,
-               injected_masks=None, sync_grads: bool = True):
+               injected_masks=None, sync_grads: bool = True, use_graph: bool | None = None):
     """One fused optimisation step (reference train.py:271-300 without the MR-STFT term).
 
     Returns the device tensor [total, vocal, accompaniment] of the UNSCALED L1 loss.  Gradients are
     written into one flat fp32 buffer (``model._flat_grad``, 9,823,313 floats); with an initialised
-    ``torch.distributed`` process group they are averaged across ranks by a single NCCL all-reduce."""
+    ``torch.distributed`` process group they are averaged across ranks over NCCL.  ``use_graph`` (default: on unless
+    dropout masks are injected or SVS_B200_TRAIN_GRAPH=0) replays the forward / loss / backward as one CUDA graph."""
     mix = mix.contiguous()
     voc = voc.contiguous()
     _check_inputs(model, mix)
     _lib.require_cuda(voc, "voc", torch.float32)
-    masks = dropout_masks(model, mix.shape[0], injected_masks)
-    flat, views = _flat_grads(model)
+    if use_graph is None:
+        use_graph = injected_masks is None and os.environ.get("SVS_B200_TRAIN_GRAPH", "1") != "0"
     with torch.no_grad():
-        mask = _raw_forward(model, mix, masks)
-        loss, grad_mask = masked_l1(mask, mix, voc, two_term, loss_scale)
-        _raw_backward(model, mix, grad_mask, masks, views)
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
-            if world > 1 and sync_grads:
-                torch.distributed.all_reduce(flat)
-                flat.div_(world)
+        flat, views = _flat_grads(model)
+        if use_graph and injected_masks is None:
+            loss = _graph_step(model, mix, voc, two_term, loss_scale)
+        else:
+            loss = _step_body(model, mix, voc, two_term, loss_scale, injected_masks)
+        if sync_grads:
+            _sync_grads(model, flat)
         for p, g in zip(param_list(model), views):
             p.grad = g
         if step:
