@@ -461,7 +461,7 @@ def run_ours(args):
                  "tflops_exact": BATCH * GFLOP_TRAIN_PER_PATCH / ms_tr,
                  "allreduce_exposed_ms": max(0.0, ms_tr - ms_tr_local) if world > 1 else 0.0,
                  "allreduce_payload_bytes": 9823313 * 4 if world > 1 else 0,
-                 "precision": training.TRAIN_PRECISION}
+                 "precision": training.train_precision(tnet), "cuda_graph": True}
         del tnet, tmix, tvoc
 
     if rank == 0:

@@ -241,6 +241,13 @@ int svs_unet_train_forward(const svs_train_plan* plan, const svs_train_layer lay
 int svs_unet_train_backward(const svs_train_plan* plan, const svs_train_layer layers[12], const float* mix,
                             const float* grad_mask, int batch, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same backward restricted to layers [first_layer, last_layer] (0 = conv1 .. 11 = deconv6), run from last to first.
+ * A data-parallel host calls it in descending segments and starts the NCCL all-reduce of a finished segment's
+ * gradients while the next segment computes (reference train.py:298 has no data parallelism). */
+int svs_unet_train_backward_layers(const svs_train_plan* plan, const svs_train_layer layers[12], const float* mix,
+                                   const float* grad_mask, int batch, void* workspace, size_t workspace_bytes,
+                                   int first_layer, int last_layer, void* stream);
+
 /* The weight-gradient contraction on its own (the wgrad half of loss.backward() through nn.Conv2d /
  * nn.ConvTranspose2d, reference model.py:47-109), TF32 on tcgen05:
  *     grad_w[(m * l_c + n) * 25 + kh * 5 + kw] = sum_{b,y,x} S[b,y,x,s_coff+m] * L[b, 2y+kh-2, 2x+kw-2, l_coff+n]

@@ -80,6 +80,8 @@ _SIGNATURES = [
                                        c_size_t, c_void_p]),
     ("svs_unet_train_backward", c_int, [c_void_p, POINTER(TrainLayer), c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                         c_void_p]),
+    ("svs_unet_train_backward_layers", c_int, [c_void_p, POINTER(TrainLayer), c_void_p, c_void_p, c_int, c_void_p,
+                                               c_size_t, c_int, c_int, c_void_p]),
     ("svs_conv_wgrad_partial_floats", c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     ("svs_conv_wgrad_tf32", c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -1022,8 +1022,16 @@ static int run_wgrad(const TrainWs& w, const svs_train_layer& L, int li, int bat
 extern "C" int svs_unet_train_backward(const svs_train_plan* plan, const svs_train_layer layers[12], const float* mix,
                                        const float* grad_mask, int batch, void* workspace, size_t workspace_bytes,
                                        void* stream) {
+  return svs_unet_train_backward_layers(plan, layers, mix, grad_mask, batch, workspace, workspace_bytes, 0, 11, stream);
+}
+
+extern "C" int svs_unet_train_backward_layers(const svs_train_plan* plan, const svs_train_layer layers[12],
+                                              const float* mix, const float* grad_mask, int batch, void* workspace,
+                                              size_t workspace_bytes, int first_layer, int last_layer, void* stream) {
   int rc = check_train_args(layers, mix, batch, workspace, workspace_bytes);
   if (rc != SVS_OK) return rc;
+  SVS_REQUIRE(first_layer >= 0 && last_layer <= 11 && first_layer <= last_layer,
+              "svs_unet_train_backward_layers: bad layer range");
   SVS_REQUIRE(grad_mask, "svs_unet_train_backward: null grad_mask");
   for (int i = 0; i < 12; ++i) {
     SVS_REQUIRE(layers[i].grad_weight && layers[i].grad_bias, "svs_unet_train_backward: grad buffers missing");
@@ -1034,7 +1042,7 @@ extern "C" int svs_unet_train_backward(const svs_train_plan* plan, const svs_tra
   const bool tc = plan != nullptr;
   // ---- deconv6: sigmoid backward, bias / weight gradient, data gradient into dcat1 (all 32 channels) ----
   // dz6 holds the forward's mask; dz6 <- grad * m (1 - m) in place
-  {
+  if (last_layer == 11) {
     const size_t n = static_cast<size_t>(batch) * 512 * 128;
     sigmoid_bwd_kernel<<<grid_for(n), 256, 0, st>>>(w.dz6, grad_mask, n, w.dz6);
     SVS_CHECK_LAUNCH("sigmoid_bwd_kernel");
@@ -1050,7 +1058,7 @@ extern "C" int svs_unet_train_backward(const svs_train_plan* plan, const svs_tra
     SVS_CHECK_LAUNCH("deconv6_dgrad_kernel");
   }
   // ---- deconv5 .. deconv1, conv6 .. conv1 ----
-  for (int li = 10; li >= 0; --li) {
+  for (int li = last_layer < 10 ? last_layer : 10; li >= first_layer; --li) {
     const LayerGeom& g = kLayers[li];
     const svs_train_layer& L = layers[li];
     const size_t N = static_cast<size_t>(batch) * g.hout * g.wout;

@@ -171,14 +171,14 @@ def _raw_forward(model, mix, masks, update_running=True):
     return mask
 
 
-def _raw_backward(model, mix, grad_mask, masks, grads):
+def _raw_backward(model, mix, grad_mask, masks, grads, first_layer=0, last_layer=11):
     b = mix.shape[0]
     ws = _workspace(model, b)
     arr = _layer_structs(model, grads, masks, need_grads=True)
     with torch.cuda.device(mix.device):
-        _lib.check(_lib.load().svs_unet_train_backward(_plan_handle(model), arr, mix.data_ptr(), grad_mask.data_ptr(), b,
-                                                       ws.data_ptr(),
-                                                       ws.numel(), _lib.stream_ptr(mix.device)),
+        _lib.check(_lib.load().svs_unet_train_backward_layers(_plan_handle(model), arr, mix.data_ptr(),
+                                                              grad_mask.data_ptr(), b, ws.data_ptr(), ws.numel(),
+                                                              first_layer, last_layer, _lib.stream_ptr(mix.device)),
                    "svs_unet_train_backward")
 
 
@@ -233,21 +233,41 @@ def masked_l1(mask, mix, voc, two_term=True, grad_scale=1.0, want_grad=True):
 
 
 
+_SPLIT_LAYER = 6       # data parallel: gradients of layers >= 6 (the decoder, 55 % of the parameters) form the first bucket
+
+
+def _step_stages(model, mix, voc, two_term, loss_scale, injected_masks, split: bool):
+    """The step as a list of stage callables: [forward + loss + backward] or, for data-parallel overlap,
+    [forward + loss + backward(decoder)], [backward(encoder)].  Stage 0 returns the loss tensor."""
+    state = {}
+
+    def head(last_first):
+        masks = dropout_masks(model, mix.shape[0], injected_masks)
+        flat, views = _flat_grads(model)
+        mask = _raw_forward(model, mix, masks)
+        loss, grad_mask = masked_l1(mask, mix, voc, two_term, loss_scale)
+        state.update(masks=masks, views=views, grad_mask=grad_mask)
+        _raw_backward(model, mix, grad_mask, masks, views, last_first, 11)
+        return loss
+
+    if not split:
+        return [lambda: head(0)]
+    return [lambda: head(_SPLIT_LAYER),
+            lambda: _raw_backward(model, mix, state["grad_mask"], state["masks"], state["views"], 0, _SPLIT_LAYER - 1)]
+
+
 def _step_body(model, mix, voc, two_term, loss_scale, injected_masks):
     """forward -> fused loss + dL/dmask -> backward into the flat gradient buffer (all on the current stream)."""
-    masks = dropout_masks(model, mix.shape[0], injected_masks)
-    flat, views = _flat_grads(model)
-    mask = _raw_forward(model, mix, masks)
-    loss, grad_mask = masked_l1(mask, mix, voc, two_term, loss_scale)
-    _raw_backward(model, mix, grad_mask, masks, views)
-    return loss
+    return _step_stages(model, mix, voc, two_term, loss_scale, injected_masks, False)[0]()
 
 
 class _StepGraph:
-    """One CUDA graph of ``_step_body`` for a fixed batch size: the step is ~250 small launches (pack, conv, BatchNorm
-    reduce / finalize / apply, dgrad, wgrad per layer), i.e. launch-bound when issued one by one from Python."""
+    """CUDA graph(s) of the step for a fixed batch size: the step is ~250 small launches (pack, conv, BatchNorm
+    reduce / finalize / apply, dgrad, wgrad per layer), i.e. launch-bound when issued one by one from Python.
+    With ``split`` the backward of the encoder is a second graph, so that the all-reduce of the decoder's
+    gradients can run under it."""
 
-    def __init__(self, model, mix, voc, two_term, loss_scale):
+    def __init__(self, model, mix, voc, two_term, loss_scale, split):
         dev = mix.device
         self.mix = torch.empty_like(mix)
         self.voc = torch.empty_like(voc)
@@ -258,17 +278,22 @@ class _StepGraph:
         with torch.cuda.stream(side):                                 # warm-up outside capture: lazy initialisation,
             for _ in range(2):                                        # workspace / flat-buffer allocation
                 _step_body(model, self.mix, self.voc, two_term, loss_scale, None)
-            # the warm-up steps must not count: restore the BatchNorm buffers they advanced
         torch.cuda.current_stream(dev).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = _step_body(model, self.mix, self.voc, two_term, loss_scale, None)
+        stages = _step_stages(model, self.mix, self.voc, two_term, loss_scale, None, split)
+        self.graphs = []
+        pool = None
+        for i, stage in enumerate(stages):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                out = stage()
+            if i == 0:
+                self.loss = out
+                pool = g.pool()                                       # later stages read tensors stage 0 allocated
+            self.graphs.append(g)
 
-    def run(self, mix, voc):
+    def load(self, mix, voc):
         self.mix.copy_(mix)
         self.voc.copy_(voc)
-        self.graph.replay()
-        return self.loss
 
 
 def _bn_buffers(model):
@@ -279,40 +304,44 @@ def _bn_buffers(model):
     return out
 
 
-def _graph_step(model, mix, voc, two_term, loss_scale):
-    key = (mix.shape[0], bool(two_term), float(loss_scale), train_precision(model), str(mix.device),
+def _world():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_world_size()
+    return 1
+
+
+def _get_graph(model, mix, voc, two_term, loss_scale, split):
+    key = (mix.shape[0], bool(two_term), float(loss_scale), train_precision(model), str(mix.device), bool(split),
            tuple(float(_layer_modules(model, i)[2].p) for i in range(6, 11)),
            tuple(p.data_ptr() for p in param_list(model)), _workspace(model, mix.shape[0]).data_ptr())
     cache = model.__dict__.setdefault("_step_graphs", {})
     g = cache.get(key)
     if g is None:
-        saved = [b.clone() for b in _bn_buffers(model)]               # capture + warm-up run real steps on the buffers
+        saved = [b.clone() for b in _bn_buffers(model)]               # the warm-up runs real steps on the buffers
         if len(cache) >= 2:
             cache.pop(next(iter(cache)))
-        g = _StepGraph(model, mix, voc, two_term, loss_scale)
+        g = _StepGraph(model, mix, voc, two_term, loss_scale, split)
         for b, v in zip(_bn_buffers(model), saved):
             b.copy_(v)
         cache[key] = g
         model._train_gen = getattr(model, "_train_gen", 0) + 1
-    return g.run(mix, voc)
+    return g
 
 
-def _sync_grads(model, flat):
-    """Data parallel: average the flat gradient buffer across ranks.  The buffer is cut into buckets that are
-    all-reduced back to back on NCCL's stream (no bucket waits for the host)."""
-    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
-        return
-    world = torch.distributed.get_world_size()
-    if world <= 1:
-        return
-    n = flat.numel()
-    bucket = 1 << 22                                                  # 16 MB of fp32 per bucket
-    works = []
-    for a in range(0, n, bucket):
-        works.append(torch.distributed.all_reduce(flat[a:min(n, a + bucket)], async_op=True))
-    for w in works:
-        w.wait()
-    flat.div_(world)
+def _all_reduce_mean(t, world):
+    """Asynchronous mean over ranks of a slice of the flat gradient buffer (NCCL: averaged inside the collective)."""
+    if torch.distributed.get_backend() == "nccl":
+        return [torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.AVG, async_op=True)], None
+    return [torch.distributed.all_reduce(t, async_op=True)], (t, world)
+
+
+def _split_offset(model):
+    """First element of the decoder's gradients in the flat buffer (parameters are ordered conv1 .. deconv6)."""
+    n = 0
+    for i in range(_SPLIT_LAYER):
+        conv, bn, _ = _layer_modules(model, i)
+        n += conv.weight.numel() + conv.bias.numel() + bn.weight.numel() + bn.bias.numel()
+    return n
 
 
 def train_step(model, mix, voc, two_term: bool = True, loss_scale: float = 1.0, step: bool = True,
@@ -329,16 +358,44 @@ def train_step(model, mix, voc, two_term: bool = True, loss_scale: float = 1.0, 
     _lib.require_cuda(voc, "voc", torch.float32)
     if use_graph is None:
         use_graph = injected_masks is None and os.environ.get("SVS_B200_TRAIN_GRAPH", "1") != "0"
+    world = _world() if sync_grads else 1
     with torch.no_grad():
         flat, views = _flat_grads(model)
-        if use_graph and injected_masks is None:
-            loss = _graph_step(model, mix, voc, two_term, loss_scale)
+        if world > 1:
+            # two stages: the decoder's gradients (the tail of the flat buffer) are all-reduced on NCCL's stream while
+            # the encoder's backward runs; only the encoder's bucket is exposed
+            off = _split_offset(model)
+            if use_graph and injected_masks is None:
+                g = _get_graph(model, mix, voc, two_term, loss_scale, True)
+                g.load(mix, voc)
+                stages = [gr.replay for gr in g.graphs]
+                loss = g.loss
+            else:
+                stages = _step_stages(model, mix, voc, two_term, loss_scale, injected_masks, True)
+                loss = None
+            out = stages[0]()
+            loss = out if loss is None else loss
+            works, fix = [], []
+            for lo, hi, stage in ((off, flat.numel(), stages[1]), (0, off, None)):
+                w, f = _all_reduce_mean(flat[lo:hi], world)
+                works += w
+                if f is not None:
+                    fix.append(f)
+                if stage is not None:
+                    stage()
+            for w in works:
+                w.wait()
+            for t, n in fix:
+                t.div_(n)
+        elif use_graph and injected_masks is None:
+            g = _get_graph(model, mix, voc, two_term, loss_scale, False)
+            g.load(mix, voc)
+            g.graphs[0].replay()
+            loss = g.loss
         else:
             loss = _step_body(model, mix, voc, two_term, loss_scale, injected_masks)
-        if sync_grads:
-            _sync_grads(model, flat)
-        for p, g in zip(param_list(model), views):
-            p.grad = g
+        for p, g_ in zip(param_list(model), views):
+            p.grad = g_
         if step:
             model.optim.step()
     return loss
