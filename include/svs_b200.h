@@ -62,6 +62,18 @@ int svs_version(void);                       /* == SVS_ABI_VERSION              
 const char* svs_last_error(void);            /* thread-local message of the last failing call   */
 int svs_device_check(int device);            /* SVS_OK iff `device` is compute capability 10.x  */
 
+/* ------------------------------------------------------------------ decode side
+ * The arithmetic of `librosa.load(path, sr=8192, mono=True)` (reference data.py:78,94) after the file bytes are
+ * read: PCM -> float (int16 / 32768), channel mean, polyphase rational resampling with scipy.signal.resample_poly's
+ * conventions (librosa's own soxr_hq filter is not reproducible: see csrc/resample.cu).
+ *   pcm        interleaved frames of `channels` samples, int16 or float32; song s = frames in_off[s] .. in_off[s+1])
+ *   out        float32 mono; song s = out[out_off[s] .. out_off[s+1]), out length = ceil(n_in * up / down)
+ *   h_poly     device float32 [up][taps]: h_poly[p][t] = h[p + t * up] of the (gain `up`) low-pass h
+ *   pre_pad, pre_remove   scipy's n_pre_pad / n_pre_remove for (len(h), up, down) */
+int svs_resample_poly(const void* pcm, int pcm_is_int16, int channels, const int64_t* in_off,
+                      const int64_t* out_off, int n_songs, int64_t max_out, int up, int down, int64_t pre_pad,
+                      int64_t pre_remove, const float* h_poly, int taps, float* out, void* stream);
+
 /* ------------------------------------------------------------------ spectral front end (S1-S3)
  * Replaces librosa.stft + librosa.magphase at reference data.py:79-81 and data.py:100-102
  * (n_fft 1024, hop 768, periodic Hann, center=True, pad_mode="constant"), batched over a ragged

@@ -52,6 +52,8 @@ _SIGNATURES = [
     ("svs_version", c_int, []),
     ("svs_last_error", c_char_p, []),
     ("svs_device_check", c_int, [c_int]),
+    ("svs_resample_poly", c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64,
+                                  c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     ("svs_stft_mag_phase", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("svs_stft_mag_phase_pcm16", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("svs_stft_complex", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),

@@ -1,7 +1,8 @@
 """Minimal WAV reader / PCM_16 writer (host I/O around the hot path; reference data.py:78,94,166 use
-librosa.load / soundfile.write, neither of which is installable here).  Decoding, mono down-mix and the
-PCM_16 write are exact; RESAMPLING is not the reference's soxr_hq ("next"):
-files whose rate differs from the target are resampled with scipy's polyphase filter and a warning."""
+librosa.load / soundfile.write, neither of which is installable here).  Decoding and the PCM_16 write are exact.
+Files whose rate differs from the target are down-mixed and resampled ON THE GPU (resample.py / svs_resample_poly: the
+polyphase Kaiser filter of scipy.signal.resample_poly); the reference's soxr_hq filter cannot be reproduced here, so
+resampled samples differ from the reference's the way any two high-quality resamplers differ (a warning says so)."""
 from __future__ import annotations
 
 import struct
@@ -57,15 +58,16 @@ def read_wav(path: str):
 def load(path: str, sr: int, mono: bool = True) -> np.ndarray:
     """Shape of ``librosa.load(path, sr=sr, mono=True)[0]``: float32 mono at ``sr``."""
     x, file_sr = read_wav(path)
+    if file_sr != sr:
+        if not mono and x.ndim == 2:
+            raise ValueError("resampling keeps mono only (reference data.py:78 loads mono)")
+        from . import resample
+        warnings.warn(f"{path}: resampling {file_sr} -> {sr} Hz with the GPU polyphase Kaiser filter "
+                      "(scipy.signal.resample_poly's design); the reference uses soxr_hq, so samples differ slightly",
+                      stacklevel=2)
+        return resample.resample(x, file_sr, sr)                        # channel mean + resampling in one kernel
     if mono and x.ndim == 2:
         x = x.mean(axis=1).astype(np.float32)
-    if file_sr != sr:
-        from math import gcd
-        import scipy.signal
-        warnings.warn(f"{path}: resampling {file_sr} -> {sr} Hz with scipy.signal.resample_poly; the reference "
-                      "uses soxr_hq (not available), so samples differ slightly", stacklevel=2)
-        g = gcd(int(sr), int(file_sr))
-        x = scipy.signal.resample_poly(x.astype(np.float64), sr // g, file_sr // g).astype(np.float32)
     return np.ascontiguousarray(x, dtype=np.float32)
 
 

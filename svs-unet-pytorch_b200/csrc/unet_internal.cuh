@@ -145,9 +145,10 @@ struct ZcLayer {
   bool enabled = false;
   bool resident = false;
   ZcSchedule sch{};
-  int n_total = 0, row_elems = 0;
+  int n_total = 0, row_elems = 0, row_bytes = 128;
   void* d_weights = nullptr;
   CUtensorMap tmap_b;
+  CUtensorMap tmap_b_half;           // box of n_total / 2 rows: one CTA's share of a multicast weight chunk
 };
 
 }  // namespace svs

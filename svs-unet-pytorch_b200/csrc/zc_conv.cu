@@ -32,8 +32,11 @@ extern int g_tc_dbg_layer;
 constexpr int kZcThreads = 192;
 constexpr int kZcBw = 8, kZcBh = 16;                 // M tile: 16 image rows x 8 pixels
 constexpr int kZcPw = kZcBw + 2, kZcPh = kZcBh + 2;  // halo slab 18 x 10 rows
-constexpr int kZcATx = kZcPw * kZcPh * 128;          // 23,040 bytes landed per slab
-constexpr int kZcASlot = 24576;                      // slot pitch (multiple of 1024)
+// kRow = bytes of one slab row (= TMA / UMMA swizzle span): 128 by default; 64 / 32 when the layer reads a channel
+// window narrower than 128 bytes (conv3's 32 skip channels of a 64-channel concat pixel, conv2's 16 of 32) so that
+// the other half of the concat buffer is neither fetched from DRAM nor carried through L2 -> shared memory.
+template <int kRow> __host__ __device__ constexpr int zc_a_tx() { return kZcPw * kZcPh * kRow; }            // bytes landed per slab
+template <int kRow> __host__ __device__ constexpr int zc_a_slot() { return (zc_a_tx<kRow>() + 1023) / 1024 * 1024; }   // slot pitch
 
 struct ZcParams {
   ZcSchedule sch;
@@ -47,9 +50,9 @@ struct ZcParams {
   long long* dbg;                // profiling: per CTA 64 clock64 stamps
 };
 
-template <int kBlockN, int kASlots, int kBSlots>
+template <int kBlockN, int kASlots, int kBSlots, int kRow>
 constexpr size_t zc_smem_bytes() {
-  return static_cast<size_t>(kASlots) * kZcASlot + static_cast<size_t>(kBSlots) * kBlockN * 128 + 1024 + 512 + 2048;
+  return static_cast<size_t>(kASlots) * zc_a_slot<kRow>() + static_cast<size_t>(kBSlots) * kBlockN * kRow + 1024 + 1024 + 2048;
 }
 
 __device__ __forceinline__ float zc_act(float v, int act) {
@@ -97,11 +100,42 @@ template <int kKMask> struct ZcConvParityTaps {   // slabs (ph, pw) = (s >> 1, s
     return (2 * dy + (s >> 1) + 2 > 4 || 2 * dx + (s & 1) + 2 > 4) ? 0 : kKMask; } };
 
 // kBSlots: ring depth when streaming, number of taps when resident
-template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps>
+__device__ __forceinline__ uint32_t zc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void zc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
+// kCluster = 2 (experiment, SVS_ZC_MCAST=1): the two CTAs of a cluster walk neighbouring tiles in lock step and SHARE
+// the streamed weight chunks: each CTA issues one half of every chunk as a multicast TMA load that lands in both
+// CTAs.  A slot may be refilled only when BOTH CTAs have consumed it: the MMA warp's commit arrives on the slot's
+// `empty` barrier of both CTAs (count 2).  Parity-green but not faster (see zc_launch_layer), so off by default.
+template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1>
 __global__ void __launch_bounds__(kZcThreads)
 zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ZcParams p) {
-  constexpr int kBBytes = kBlockN * 128;
+  static_assert(kCluster == 1 || kCluster == 2, "CTA pairs only");
+  constexpr uint16_t kMask = (1u << kCluster) - 1u;
+  constexpr int kBBytes = kBlockN * kRow;
+  constexpr int kZcATx = zc_a_tx<kRow>(), kZcASlot = zc_a_slot<kRow>();
+  constexpr int kKSteps = kRow / 32;                              // UMMA K = 32 bytes
+  constexpr uint64_t kLayout = kRow == 128 ? 2 : (kRow == 64 ? 4 : 6);   // UMMA layout type of the swizzle span
   constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;
   constexpr int kTmemCols = 2 * kAccCols;
   constexpr int kNBar = 2 * kBSlots + 2 * kASlots + 4;
@@ -118,10 +152,10 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto empty_a = [&](int s) { return bar_base + 8u * (2 * kBSlots + kASlots + s); };
   auto tmem_full = [&](int s) { return bar_base + 8u * (2 * kBSlots + 2 * kASlots + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * kBSlots + 2 * kASlots + 2 + s); };
-  static_assert(kNBar * 8 + 8 <= 512, "barrier area");
+  static_assert(kNBar * 8 + 8 <= 1024, "barrier area");
   const uint32_t tmem_slot = bar_base + 8u * kNBar;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * kNBar);
-  float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 512);
+  float* sbias = reinterpret_cast<float*>(smem_gen + bar_off + 1024);
   for (int i = threadIdx.x; i < p.cout_phase; i += kZcThreads) sbias[i] = __ldg(&p.bias[i]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,7 +165,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int n_slabs = p.sch.n_slabs, n_taps = p.sch.n_taps;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kBSlots; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    for (int s = 0; s < kBSlots; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), kCluster); }
     for (int s = 0; s < kASlots; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), 4); }
     fence_barrier_init();
@@ -142,6 +176,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) zc_cluster_sync();    // the partner's barriers are initialised before anything lands in them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -184,7 +219,13 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               mbar_wait(empty_b(bs), ((jb / kBSlots) & 1) ^ 1);
               if (elect_one_sync()) {
                 mbar_expect_tx(full_b(bs), kBBytes);
-                tma_load_2d(b_base + bs * kBBytes, &tmap_b, full_b(bs), next_tap * p.row_elems, 0);
+                if constexpr (kCluster == 1) {
+                  tma_load_2d(b_base + bs * kBBytes, &tmap_b, full_b(bs), next_tap * p.row_elems, 0);
+                } else {                          // my half of the rows, into both CTAs (tmap_b's box is kBlockN / 2 rows)
+                  const int half = static_cast<int>(zc_cluster_rank());
+                  tma_load_2d_mcast(b_base + bs * kBBytes + half * (kBBytes / 2), &tmap_b, full_b(bs), next_tap * p.row_elems,
+                                    half * (kBlockN / 2), kMask);
+                }
               }
               __syncwarp();
             }
@@ -216,7 +257,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             const uint32_t a_base = smem_base + slot * kZcASlot;
             const uint64_t da0 = static_cast<uint64_t>((a_base & 0x3FFFF) >> 4) | (1ull << 16) |
-                                 (static_cast<uint64_t>((kZcPw * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+                                 (static_cast<uint64_t>((kZcPw * kRow) >> 4) << 32) | (1ull << 46) | (kLayout << 61);
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
 #pragma unroll
@@ -233,17 +274,20 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   tc_fence_after();
                   b_addr = b_base + bs * kBBytes;
                 }
-                const uint64_t db = make_smem_desc<128>(b_addr);
-                const uint32_t a_off16 = static_cast<uint32_t>(((dy + 1) * kZcPw + (dx + 1)) * 128) >> 4;
+                const uint64_t db = make_smem_desc<kRow>(b_addr);
+                const uint32_t a_off16 = static_cast<uint32_t>(((dy + 1) * kZcPw + (dx + 1)) * kRow) >> 4;
                 if (elect_one_sync()) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
+                  for (int k = 0; k < kKSteps; ++k) {
                     if (kmask & (1 << k)) {
                       umma<kTf32>(tmem_d, da0 + a_off16 + 2u * k, db + 2u * k, idesc, first_mma ? 0u : 1u);
                       first_mma = false;
                     }
                   }
-                  if (!p.resident) umma_commit(empty_b(bs));
+                  if (!p.resident) {
+                    if constexpr (kCluster == 1) umma_commit(empty_b(bs));
+                    else umma_commit_mcast(empty_b(bs), kMask);
+                  }
                 }
                 __syncwarp();
                 first_mma = false;
@@ -274,20 +318,23 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tc_fence_after();
               b_addr = b_base + bs * kBBytes;
             }
-            const uint32_t a_addr = a_base + ((p.sch.tap_dy[tap] + 1) * kZcPw + (p.sch.tap_dx[tap] + 1)) * 128;
-            const uint32_t sbo = kZcPw * 128;
-            // SW128 K-major; 8-row groups (one image row) are 10 slab rows = 1280 B apart; base_offset 0
+            const uint32_t a_addr = a_base + ((p.sch.tap_dy[tap] + 1) * kZcPw + (p.sch.tap_dx[tap] + 1)) * kRow;
+            const uint32_t sbo = kZcPw * kRow;
+            // K-major; 8-row groups (one image row) are 10 slab rows apart; base_offset 0
             const uint64_t da = static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4) | (1ull << 16) |
-                                (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
-            const uint64_t db = make_smem_desc<128>(b_addr);
+                                (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (kLayout << 61);
+            const uint64_t db = make_smem_desc<kRow>(b_addr);
             const int kmask = p.sch.tap_kmask[tap];
             const int k_lo = __ffs(kmask) - 1;             // first active k-step of this tap
             if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < kKSteps; ++k) {
                 if (kmask & (1 << k)) umma<kTf32>(tmem_d, da + 2u * k, db + 2u * k, idesc, (first != 0u || k != k_lo) ? 1u : 0u);
               }
-              if (!p.resident) umma_commit(empty_b(bs));
+              if (!p.resident) {
+                if constexpr (kCluster == 1) umma_commit(empty_b(bs));
+                else umma_commit_mcast(empty_b(bs), kMask);
+              }
             }
             __syncwarp();
             first = 1u;
@@ -366,6 +413,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) zc_cluster_sync();    // the partner's last commits / loads target this CTA's shared memory
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   if (warp == 1) {
     tc_fence_after();
@@ -415,8 +463,8 @@ __global__ void zc_pack_weights_kernel(const float* __restrict__ w_fold /*[25][c
 }
 
 // host: is k-step `k` of tap (slab s, dy, dx) non-zero for any output column?
-static bool kstep_active(const ZcSchedule& sch, const LayerGeom& g, int ct, int row_elems, int s, int dy, int dx, int k) {
-  const int kel = row_elems / 4;
+static bool kstep_active(const ZcSchedule& sch, const LayerGeom& g, int ct, int row_elems, int ksteps, int s, int dy, int dx, int k) {
+  const int kel = row_elems / ksteps;
   for (int e = k * kel; e < (k + 1) * kel; ++e) {
     const int abs_c = sch.slab_c[s] + e;
     if (!g.transposed) {
@@ -447,8 +495,18 @@ int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
   if (gh % kZcBh != 0 || gw % kZcBw != 0) return SVS_OK;
   const int n_total = g.transposed ? 4 * g.cout : g.cout;
   if (n_total != 32 && n_total != 64 && n_total != 128 && n_total != 256) return SVS_OK;
-  const int row = 128 / es;
   const int ct = kBufGeom[g.in_buf].c;
+  // slab row = 128 bytes of channels, or exactly the layer's own channel window when that is narrower (conv2, conv3:
+  // the skip half of a concat pixel): the other half is then never fetched
+  static const bool narrow_on = [] { const char* e = std::getenv("SVS_ZC_NARROW"); return !(e && e[0] == '0'); }();
+  int row_bytes = 128;
+  if (narrow_on && !g.transposed && g.cin * es < 128 && (g.cin * es == 32 || g.cin * es == 64) &&
+      (g.in_coff * es) % (g.cin * es) == 0 && li == 2)
+    row_bytes = g.cin * es;          // conv3 only: conv2 is DRAM bound either way (32-byte sectors of 64-byte DRAM
+                                     // atoms save nothing) and TMA issues ~5 cycles per slab row whatever its width,
+                                     // so 32-byte rows were slower there (measured: 4,600 vs 3,750 cycles per tile)
+  const int row = row_bytes / es;
+  const int ksteps = row_bytes / 32;
   ZcSchedule sch{};
   auto add_slab = [&](int c, int ph) { sch.slab_c[sch.n_slabs] = c; sch.slab_ph[sch.n_slabs] = ph; return sch.n_slabs++; };
   if (!g.transposed) {
@@ -472,7 +530,7 @@ int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
     for (int dy = -1; dy <= 1; ++dy)
       for (int dx = -1; dx <= 1; ++dx) {
         int kmask = 0;
-        for (int k = 0; k < 4; ++k) kmask |= kstep_active(sch, g, ct, row, s, dy, dx, k) ? (1 << k) : 0;
+        for (int k = 0; k < ksteps; ++k) kmask |= kstep_active(sch, g, ct, row, ksteps, s, dy, dx, k) ? (1 << k) : 0;
         if (!kmask) continue;
         if (sch.n_taps >= kZcMaxTaps) return SVS_OK;
         sch.tap_slab[sch.n_taps] = static_cast<signed char>(s);
@@ -484,9 +542,11 @@ int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
   z.sch = sch;
   z.n_total = n_total;
   z.row_elems = row;
-  // resident weights when all tap chunks fit beside a 4-slab ring
-  const size_t w_bytes = static_cast<size_t>(sch.n_taps) * n_total * 128;
-  z.resident = w_bytes <= 80 * 1024 && (sch.n_taps == 9 || sch.n_taps == 15);
+  z.row_bytes = row_bytes;
+  // resident weights when all tap chunks fit beside the slab ring
+  const size_t w_bytes = static_cast<size_t>(sch.n_taps) * n_total * row_bytes;
+  z.resident = (w_bytes <= 80 * 1024 && (sch.n_taps == 9 || sch.n_taps == 15)) ||
+               (row_bytes < 128 && w_bytes <= 104 * 1024 && sch.n_taps == 25);
   SVS_CUDA_TRY(cudaMalloc(&z.d_weights, w_bytes));
   ZcPackArgs a{};
   a.sch = sch; a.row_elems = row; a.ct = ct; a.in_coff = g.in_coff; a.cin = g.cin; a.cout = g.cout;
@@ -497,9 +557,12 @@ int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
   else zc_pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(plan->w_fold[li], a, static_cast<__nv_bfloat16*>(z.d_weights));
   SVS_CHECK_LAUNCH("zc_pack_weights_kernel");
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(sch.n_taps) * row, static_cast<cuuint64_t>(n_total)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(sch.n_taps) * 128};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(sch.n_taps) * row_bytes};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(row), static_cast<cuuint32_t>(n_total)};
-  int rc = encode_tensor_map(&z.tmap_b, tf32, 2, z.d_weights, dims, strides, box, 128);
+  int rc = encode_tensor_map(&z.tmap_b, tf32, 2, z.d_weights, dims, strides, box, row_bytes);
+  if (rc != SVS_OK) return rc;
+  const cuuint32_t box_half[2] = {static_cast<cuuint32_t>(row), static_cast<cuuint32_t>(n_total / 2)};
+  rc = encode_tensor_map(&z.tmap_b_half, tf32, 2, z.d_weights, dims, strides, box_half, row_bytes);
   if (rc != SVS_OK) return rc;
   z.enabled = true;
   return SVS_OK;
@@ -513,10 +576,10 @@ void zc_free_layers(svs_unet_plan* plan) {
   }
 }
 
-template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps>
+template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1>
 static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcParams& p, cudaStream_t st) {
-  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps>;
-  constexpr size_t smem = zc_smem_bytes<kBlockN, kASlots, kBSlots>();
+  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps, kRow, kCluster>;
+  constexpr size_t smem = zc_smem_bytes<kBlockN, kASlots, kBSlots, kRow>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
   SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;
@@ -526,7 +589,21 @@ static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcPar
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
   if (grid > p.m_tiles) grid = p.m_tiles;
-  SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, ta, tb, p));
+  if constexpr (kCluster == 1) {
+    SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, ta, tb, p));
+  } else {
+    grid &= ~1;                                      // whole CTA pairs; the caller guarantees an even tile count
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kZcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    SVS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  }
   return SVS_OK;
 }
 
@@ -547,7 +624,7 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
       strides[0] = ct * es; strides[1] = W * ct * es; strides[2] = W * ct * es; strides[3] = H * W * ct * es;
     }
     const cuuint32_t box[5] = {static_cast<cuuint32_t>(z.row_elems), kZcPw, 1, kZcPh, 1};
-    int rc = encode_tensor_map(&ta, tf32, 5, ws.buf[g.in_buf], dims, strides, box, 128);
+    int rc = encode_tensor_map(&ta, tf32, 5, ws.buf[g.in_buf], dims, strides, box, z.row_bytes);
     if (rc != SVS_OK) return rc;
   }
   ZcParams p{};
@@ -570,8 +647,32 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   const int n = z.n_total;
   // bf16 layers of the reference network get compile-time tap tables; anything else (TF32 rows are 32
   // channels wide, so the slab/tap sets differ) runs the same kernel with the runtime schedule
+#define SVS_ZC_NARROW(TF, LI, N, AS, BS, TAPS, ROW)                                                     \
+  if (tf32 == TF && li == LI && n == N && z.resident && z.row_bytes == ROW && z.sch.n_slabs == TAPS::kSlabs && \
+      z.sch.n_taps == BS) {                                                                                \
+    if constexpr (TF) return zc_launch_t<float, true, N, AS, BS, TAPS, ROW>(ta, z.tmap_b, p, st);          \
+    else return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS, ROW>(ta, z.tmap_b, p, st);              \
+  }
+  // narrow slab rows (the layer's own channel window), all 25 tap chunks resident
+  SVS_ZC_NARROW(false, 1, 32, 8, 25, ZcConvParityTaps<0x1>, 32)      // conv2: 16 bf16 channels = 32-byte rows, 2 CTAs / SM
+  SVS_ZC_NARROW(false, 2, 64, 6, 25, ZcConvParityTaps<0x3>, 64)      // conv3: 32 bf16 channels = 64-byte rows, 100 KB of weights
+  SVS_ZC_NARROW(true, 1, 32, 4, 25, ZcConvParityTaps<0x3>, 64)       // conv2 TF32: 16 fp32 channels = 64-byte rows
+#undef SVS_ZC_NARROW
+  if (z.row_bytes != 128) return fail(SVS_ERR_NOT_IMPLEMENTED, "zc_launch_layer: no narrow-row instantiation");
+  // streamed weights shared by CTA pairs (multicast halves): OFF by default.  Measured at batch 64 / 512 (bf16:
+  // 225.7 vs 224.3 us, TF32: 458 vs 427 us per 64 patches): the pair's lock step costs as much as the halved weight
+  // requests save — the kernels are bound by bytes INTO an SM's shared memory (~58 B/clk), which a multicast does not
+  // reduce; only splitting B across the pair (cta_group::2) or two M tiles per weight pass would.
+  static const bool mcast_on = [] { const char* e = std::getenv("SVS_ZC_MCAST"); return e && e[0] == '1'; }();
+  const bool pair = mcast_on && !z.resident && p.m_tiles % 2 == 0 && p.m_tiles >= 2;
 #define SVS_ZC_STATIC(TF, LI, N, AS, BS, RES, TAPS)                                                 \
   if (tf32 == TF && li == LI && n == N && z.resident == RES && z.sch.n_slabs == TAPS::kSlabs) {       \
+    if constexpr (!RES) {                                                                             \
+      if (pair) {                                                                                     \
+        if constexpr (TF) return zc_launch_t<float, true, N, AS, BS, TAPS, 128, 2>(ta, z.tmap_b_half, p, st);          \
+        else return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS, 128, 2>(ta, z.tmap_b_half, p, st);              \
+      }                                                                                               \
+    }                                                                                                 \
     if constexpr (TF) return zc_launch_t<float, true, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);          \
     else return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);              \
   }

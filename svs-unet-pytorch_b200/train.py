@@ -5,9 +5,10 @@ Differences, all outside the kernels' arithmetic and stated here so they are not
 * the loss is ``alpha_L1 * (L1(mask*mix, voc) + L1((1-mask)*mix, clamp(mix-voc, 0)))`` (train.py:275-283,296
   with crit = nn.L1Loss, reference config.py:33,44).  The MR-STFT term of train.py:287-296 needs
   ``auraloss`` (not installable here) and is out of the hot-path scope ("next").
-* ``SpectrogramDataset`` keeps every song's spectrogram resident in HBM and cuts the random 128-frame
-  crops on the device (the reference re-reads four .npy files per sample in 8 DataLoader workers,
-  train.py:86-143,182); the phase files are not needed without the MR-STFT term.
+* ``SpectrogramDataset`` keeps every song's spectrogram resident in HBM (frame-major, all songs back to back) and
+  cuts the random 128-frame crops of a whole batch with two svs_patches_gather launches (the reference re-reads four
+  .npy files per sample in 8 DataLoader workers, train.py:86-143,182); the phase files are only needed by the
+  MR-STFT term.
 * with WORLD_SIZE > 1 (torchrun) the step is data parallel: one NCCL all-reduce of the flat gradient
   buffer per step; rank 0 writes checkpoints and logs.  The reference is single device.
 """
@@ -21,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib, training
-from .config import INPUT_LEN, SAMPLES_PER_SONG
+from .config import INPUT_LEN, N_BINS, SAMPLES_PER_SONG
 from .model import UNet
 
 alpha_L1 = 166.66          # reference train.py:24
@@ -41,12 +42,25 @@ class SpectrogramDataset:
         names = sorted(f for f in os.listdir(self.mixture_path) if f.endswith("_spec.npy"))
         self.file_names = [f for f in names if os.path.exists(os.path.join(self.vocal_path, f))]
         self.device = torch.device(device)
-        self.mix, self.voc = [], []
-        for f in self.file_names:                                    # [T][512] on the device, DC dropped
-            m = np.load(os.path.join(self.mixture_path, f))[1:, :]
-            v = np.load(os.path.join(self.vocal_path, f))[1:, :]
-            self.mix.append(torch.from_numpy(np.ascontiguousarray(m, dtype=np.float32)).to(self.device))
-            self.voc.append(torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(self.device))
+        # Every song's (513, T) spectrogram is kept in HBM in FRAME-MAJOR form [T][513] — the bytes of the
+        # Fortran-ordered array data.py writes — all songs back to back, so a random 128-frame crop (DC row dropped,
+        # zero padded when the song is shorter) is exactly one patch of svs_patches_gather and a whole batch is
+        # two kernel launches instead of 2 x B Python slices and a stack.
+        mix, voc, frames = [], [], []
+        for f in self.file_names:
+            m = np.load(os.path.join(self.mixture_path, f))
+            v = np.load(os.path.join(self.vocal_path, f))
+            t = min(m.shape[1], v.shape[1])
+            mix.append(np.ascontiguousarray(m[:, :t].T, dtype=np.float32))
+            voc.append(np.ascontiguousarray(v[:, :t].T, dtype=np.float32))
+            frames.append(t)
+        self.frames = frames
+        self.frame_off = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+        if frames:
+            self.mix_all = torch.from_numpy(np.concatenate(mix, axis=0)).to(self.device)
+            self.voc_all = torch.from_numpy(np.concatenate(voc, axis=0)).to(self.device)
+        else:
+            self.mix_all = self.voc_all = torch.zeros((0, N_BINS), dtype=torch.float32, device=self.device)
         self.rng = random.Random(seed)
         print(f"[{os.path.basename(path)}] loaded {len(self.file_names)} songs, {samples_per_song} samples per "
               f"song per epoch, {len(self)} items.")
@@ -54,15 +68,24 @@ class SpectrogramDataset:
     def __len__(self):
         return len(self.file_names) * self.samples_per_song
 
+    def crop_starts(self, indices):
+        """(song, first frame, valid frames) of every item: reference train.py:112-131 (shared start for mixture and
+        vocal, one randint per item that is longer than a patch)."""
+        out = []
+        for idx in indices:
+            s = idx % len(self.file_names)
+            cur = self.frames[s]
+            if cur > INPUT_LEN:
+                start = self.rng.randint(0, cur - INPUT_LEN)          # train.py:116
+                out.append((s, start, INPUT_LEN))
+            else:
+                out.append((s, 0, cur))                               # zero padded on the right (train.py:124-131)
+        return out
+
     def item(self, idx):
-        s = idx % len(self.file_names)
-        mix, voc = self.mix[s], self.voc[s]
-        cur = mix.shape[1]
-        if cur > INPUT_LEN:
-            start = self.rng.randint(0, cur - INPUT_LEN)              # train.py:116 (shared start)
-            return mix[:, start:start + INPUT_LEN], voc[:, start:start + INPUT_LEN]
-        pad = INPUT_LEN - cur
-        return torch.nn.functional.pad(mix, (0, pad)), torch.nn.functional.pad(voc, (0, pad))
+        """One (mix, voc) pair of shape (512, 128) — the reference's __getitem__ without the phase arrays."""
+        mix, voc = self.crop_batch([idx])
+        return mix[0, 0], voc[0, 0]
 
     def epoch_order(self, batch_size, shuffle=True, rank=0, world=1, epoch_seed=None):
         """Item indices this rank visits in one epoch.  Single process: the reference's DataLoader order
@@ -87,10 +110,15 @@ class SpectrogramDataset:
             yield self.crop_batch(order[a:a + batch_size])
 
     def crop_batch(self, indices):
-        """(mix, voc) float32 (B,1,512,128) for the given items (reference train.py:100-143 per item)."""
-        items = [self.item(i) for i in indices]
-        mix = torch.stack([m for m, _ in items]).unsqueeze(1).contiguous()
-        voc = torch.stack([v for _, v in items]).unsqueeze(1).contiguous()
+        """(mix, voc) float32 (B,1,512,128) for the given items (reference train.py:100-143 per item), cut on the
+        device by svs_patches_gather."""
+        crops = self.crop_starts(indices)
+        offs = np.asarray([(self.frame_off[s] + start) * N_BINS + 1 for s, start, _ in crops], dtype=np.int64)
+        valid = np.asarray([n for _, _, n in crops], dtype=np.int32)
+        d_off = torch.from_numpy(offs).to(self.device, non_blocking=True)
+        d_valid = torch.from_numpy(valid).to(self.device, non_blocking=True)
+        mix = _lib.patches_gather_raw(self.mix_all, d_off, d_valid, None)
+        voc = _lib.patches_gather_raw(self.voc_all, d_off, d_valid, None)
         return mix, voc
 
     def n_batches(self, batch_size, world=1):

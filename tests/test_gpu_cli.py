@@ -123,3 +123,35 @@ def test_train_cli_one_epoch(tmp_path, monkeypatch):
     train.main(["--train_folder", spec_dir, "--valid_folder", "missing", "--label", "t", "--epoch", "3",
                 "--batch_size", "4", "--load_path", str(tmp_path / "CKPT" / "svs_t.pth")])
     assert torch.load(str(tmp_path / "CKPT" / "svs_t.pth"), map_location="cpu")["epoch"] == 3
+
+
+def test_training_crops_match_the_reference_getitem(tmp_path):
+    # SpectrogramDataset.crop_batch (two svs_patches_gather launches per batch) against a numpy restatement of the
+    # reference's __getitem__ (train.py:99-131: DC row dropped, random shared start, zero padding when short)
+    import random
+    spec_dir = tmp_path / "spec"
+    rng = np.random.default_rng(0)
+    lens = [300, 128, 57, 129]
+    for sub in ("mixture", "vocal"):
+        os.makedirs(spec_dir / sub)
+    specs = {}
+    for i, t in enumerate(lens):
+        for sub in ("mixture", "vocal"):
+            a = np.asfortranarray(rng.random((513, t), dtype=np.float32))          # data.py writes F-ordered (513, T)
+            np.save(spec_dir / sub / f"{i:04d}_song_spec.npy", a)
+            specs[(sub, i)] = a
+    ds = train.SpectrogramDataset(str(spec_dir), samples_per_song=3, device="cuda", seed=5)
+    ref_rng = random.Random(5)
+    idx = [0, 5, 2, 7, 3, 9, 10, 1]
+    mix, voc = ds.crop_batch(idx)
+    assert mix.shape == voc.shape == (8, 1, 512, 128)
+    for k, i in enumerate(idx):
+        s = i % 4
+        m, v = specs[("mixture", s)][1:, :], specs[("vocal", s)][1:, :]
+        cur = m.shape[1]
+        if cur > 128:
+            start = ref_rng.randint(0, cur - 128)
+            m, v = m[:, start:start + 128], v[:, start:start + 128]
+        else:
+            m, v = np.pad(m, ((0, 0), (0, 128 - cur))), np.pad(v, ((0, 0), (0, 128 - cur)))
+        assert np.array_equal(mix[k, 0].cpu().numpy(), m) and np.array_equal(voc[k, 0].cpu().numpy(), v), k

@@ -45,6 +45,8 @@ VARIANTS = {
     "conv1_im2col": {"SVS_C1Z_DISABLE": "1"},                           # conv1_tc_kernel instead of conv1_zc_kernel
     "wide_tiles_large_batch": {"SVS_TEST_BATCH": "160"},                # conv5 / conv6 / deconv1 on 128 x 256 tiles
     "narrow_tiles_large_batch": {"SVS_TEST_BATCH": "160", "SVS_TC_NO_WIDE": "1"},
+    "full_width_slab_rows": {"SVS_ZC_NARROW": "0"},
+    "weight_multicast_pairs": {"SVS_ZC_MCAST": "1"},                    # CTA pairs share streamed weight chunks (TMA multicast)                     # conv2 / conv3 on 128-byte rows (both concat halves)
 }
 
 

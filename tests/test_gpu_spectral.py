@@ -138,3 +138,30 @@ def test_pcm16_boundary_matches_the_float_path():
     ref = np.clip(np.rint(norm.cpu().numpy().astype(np.float64) * 32767.0), -32768, 32767)
     assert np.abs(q.cpu().numpy().astype(np.int64) - ref.astype(np.int64)).max() <= 1   # fp32 vs fp64 product at ties
     assert int(q.abs().max()) == int(round(0.9 * 32767))
+
+
+def test_gpu_resampler_matches_scipy_polyphase_oracle():
+    # 44.1 kHz stereo PCM_16 -> mono 8192 Hz (data.py:78) on the GPU against
+    # scipy.signal.resample_poly in float64 after the same / 32768 and channel mean; ragged two-song batch
+    from oracle import resample_oracle
+    from svs_unet_pytorch_b200 import resample
+    rng = np.random.default_rng(7)
+    t = np.arange(44100 * 3) / 44100.0
+    s1 = np.stack([0.4 * np.sin(2 * np.pi * 440 * t) + 0.05 * rng.standard_normal(len(t)),
+                   0.3 * np.sin(2 * np.pi * 1000 * t) + 0.05 * rng.standard_normal(len(t))], axis=1)
+    s2 = 0.3 * rng.standard_normal((50001, 2))
+    pcm = [np.clip(np.rint(s * 32767), -32768, 32767).astype(np.int16) for s in (s1, s2)]
+    dev_pcm = torch.from_numpy(np.concatenate([p.reshape(-1) for p in pcm])).cuda()
+    out, lens = resample.resample_songs(dev_pcm, [len(p) for p in pcm], 2, 44100, 8192)
+    out = out.cpu().numpy()
+    off = 0
+    for p, n in zip(pcm, lens):
+        ref = resample_oracle.load_like(p, 44100, 8192)
+        assert n == len(ref)
+        assert np.abs(out[off:off + n] - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+        off += n
+    # float32 mono input, another ratio (48 kHz -> 8192 Hz), through the numpy-shaped call
+    x = (0.2 * rng.standard_normal(48000)).astype(np.float32)
+    y = resample.resample(x, 48000, 8192)
+    ref = resample_oracle.load_like(x, 48000, 8192)
+    assert y.shape == ref.shape and np.abs(y - ref).max() <= 2e-6
