@@ -2,9 +2,11 @@
 sm_100a training kernels.
 
 Differences, all outside the kernels' arithmetic and stated here so they are not silent:
-* the loss is ``alpha_L1 * (L1(mask*mix, voc) + L1((1-mask)*mix, clamp(mix-voc, 0)))`` (train.py:275-283,296
-  with crit = nn.L1Loss, reference config.py:33,44).  The MR-STFT term of train.py:287-296 needs
-  ``auraloss`` (not installable here) and is out of the hot-path scope ("next").
+* the loss is ``alpha_L1 * (L1(mask*mix, voc) + L1((1-mask)*mix, clamp(mix-voc, 0))) + alpha_MR * MRSTFT`` (train.py:275-296
+  with crit = nn.L1Loss, reference config.py:33,44).  ``--mr_stft 1`` (default, the reference's objective) adds the
+  MR-STFT term through ``losses.py`` (a restatement of auraloss 0.4.0 on torch.stft / torch.istft; the UNet under it is
+  the sm_100a autograd path); ``--mr_stft 0`` trains on the L1 term alone with the fused CUDA-graph step
+  (training.train_step — the configuration BASELINE configs[4] names and bench.py times).
 * ``SpectrogramDataset`` keeps every song's spectrogram resident in HBM (frame-major, all songs back to back) and
   cuts the random 128-frame crops of a whole batch with two svs_patches_gather launches (the reference re-reads four
   .npy files per sample in 8 DataLoader workers, train.py:86-143,182); the phase files are only needed by the
@@ -22,10 +24,11 @@ import numpy as np
 import torch
 
 from . import _lib, training
-from .config import INPUT_LEN, N_BINS, SAMPLES_PER_SONG
+from .config import INPUT_LEN, N_BINS, SAMPLE_RATE, SAMPLES_PER_SONG
 from .model import UNet
 
 alpha_L1 = 166.66          # reference train.py:24
+alpha_MR = 0.66            # reference train.py:25
 
 
 class SpectrogramDataset:
@@ -33,7 +36,8 @@ class SpectrogramDataset:
     ``<path>/vocal/`` file; ``len = n_songs * samples_per_song``; item = random 128-frame crop (shared
     start for mixture and vocal), DC row dropped, zero padded when the song is shorter."""
 
-    def __init__(self, path, samples_per_song=SAMPLES_PER_SONG, device="cuda", seed=None):
+    def __init__(self, path, samples_per_song=SAMPLES_PER_SONG, device="cuda", seed=None, with_phase=False):
+        self.with_phase = with_phase
         self.mixture_path = os.path.join(path, "mixture")
         self.vocal_path = os.path.join(path, "vocal")
         self.samples_per_song = samples_per_song
@@ -46,7 +50,7 @@ class SpectrogramDataset:
         # Fortran-ordered array data.py writes — all songs back to back, so a random 128-frame crop (DC row dropped,
         # zero padded when the song is shorter) is exactly one patch of svs_patches_gather and a whole batch is
         # two kernel launches instead of 2 x B Python slices and a stack.
-        mix, voc, frames = [], [], []
+        mix, voc, frames, mph, vph = [], [], [], [], []
         for f in self.file_names:
             m = np.load(os.path.join(self.mixture_path, f))
             v = np.load(os.path.join(self.vocal_path, f))
@@ -54,11 +58,18 @@ class SpectrogramDataset:
             mix.append(np.ascontiguousarray(m[:, :t].T, dtype=np.float32))
             voc.append(np.ascontiguousarray(v[:, :t].T, dtype=np.float32))
             frames.append(t)
+            if with_phase:                                            # train.py:92-106: angle of the *_phase.npy arrays
+                pn = f.replace("_spec.npy", "_phase.npy")
+                mph.append(np.ascontiguousarray(np.angle(np.load(os.path.join(self.mixture_path, pn)))[:, :t].T, dtype=np.float32))
+                vph.append(np.ascontiguousarray(np.angle(np.load(os.path.join(self.vocal_path, pn)))[:, :t].T, dtype=np.float32))
         self.frames = frames
         self.frame_off = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
         if frames:
             self.mix_all = torch.from_numpy(np.concatenate(mix, axis=0)).to(self.device)
             self.voc_all = torch.from_numpy(np.concatenate(voc, axis=0)).to(self.device)
+            if with_phase:
+                self.mix_phase_all = torch.from_numpy(np.concatenate(mph, axis=0)).to(self.device)
+                self.voc_phase_all = torch.from_numpy(np.concatenate(vph, axis=0)).to(self.device)
         else:
             self.mix_all = self.voc_all = torch.zeros((0, N_BINS), dtype=torch.float32, device=self.device)
         self.rng = random.Random(seed)
@@ -83,9 +94,8 @@ class SpectrogramDataset:
         return out
 
     def item(self, idx):
-        """One (mix, voc) pair of shape (512, 128) — the reference's __getitem__ without the phase arrays."""
-        mix, voc = self.crop_batch([idx])
-        return mix[0, 0], voc[0, 0]
+        """One item of shape (512, 128) per array — the reference's __getitem__ (phases only with with_phase)."""
+        return tuple(t[0, 0] for t in self.crop_batch([idx]))
 
     def epoch_order(self, batch_size, shuffle=True, rank=0, world=1, epoch_seed=None):
         """Item indices this rank visits in one epoch.  Single process: the reference's DataLoader order
@@ -119,6 +129,9 @@ class SpectrogramDataset:
         d_valid = torch.from_numpy(valid).to(self.device, non_blocking=True)
         mix = _lib.patches_gather_raw(self.mix_all, d_off, d_valid, None)
         voc = _lib.patches_gather_raw(self.voc_all, d_off, d_valid, None)
+        if self.with_phase:
+            return (mix, voc, _lib.patches_gather_raw(self.mix_phase_all, d_off, d_valid, None),
+                    _lib.patches_gather_raw(self.voc_phase_all, d_off, d_valid, None))
         return mix, voc
 
     def n_batches(self, batch_size, world=1):
@@ -137,6 +150,8 @@ def build_parser():
     p.add_argument("--batch_size", type=int, default=2)
     p.add_argument("--valid_folder", type=str, default="unet_spectrograms/valid")
     p.add_argument("--val_interval", type=int, default=20)
+    p.add_argument("--mr_stft", type=int, default=1,
+                   help="1: reference objective (L1 + MR-STFT, train.py:287-296); 0: L1 only, fused CUDA-graph step")
     return p
 
 
@@ -149,17 +164,35 @@ def make_checkpoint(model, epoch, scheduler=None):
     return ckpt
 
 
+def full_objective(model, batch, mr_loss_fn):
+    """reference train.py:274-296 on one batch (mix, voc, mix_phase, voc_phase): returns (total, l1, mr)."""
+    from . import losses
+    mix, voc, mix_phase, voc_phase = batch
+    mask = model(mix)                                                # train mode: autograd over the sm_100a kernels
+    pred_vocal = mask * mix
+    l1 = (pred_vocal - voc).abs().mean() + ((1 - mask) * mix - torch.clamp(mix - voc, min=0.0)).abs().mean()
+    mr = mr_loss_fn(losses.specific_istft(pred_vocal, mix_phase), losses.specific_istft(voc, voc_phase))
+    return alpha_L1 * l1 + alpha_MR * mr, l1, mr
+
+
 @torch.no_grad()
-def validate(model, dataset, batch_size, rank=0, world=1):
+def validate(model, dataset, batch_size, rank=0, world=1, mr_loss_fn=None):
     model.eval()
     total, n = 0.0, 0
-    for mix, voc in dataset.batches(batch_size, shuffle=False, rank=rank, world=world):
+    dev = next(model.parameters()).device
+    for batch in dataset.batches(batch_size, shuffle=False, rank=rank, world=world):
+        mix, voc = batch[0], batch[1]
         mask = model(mix)
         loss, _ = training.masked_l1(mask, mix, voc, two_term=True, want_grad=False)
-        total += alpha_L1 * float(loss[0])
+        val = alpha_L1 * float(loss[0])
+        if mr_loss_fn is not None:                                   # train.py:318-341
+            from . import losses
+            val += alpha_MR * float(mr_loss_fn(losses.specific_istft(mask * mix, batch[2]),
+                                               losses.specific_istft(voc, batch[3])))
+        total += val
         n += 1
     if world > 1:                                                    # every rank sees the same validation loss
-        acc = torch.tensor([total, float(n)], dtype=torch.float64, device=mix.device if n else "cuda")
+        acc = torch.tensor([total, float(n)], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(acc)
         total, n = float(acc[0]), int(acc[1])
     return total / max(n, 1)
@@ -184,10 +217,16 @@ def main(argv=None):
     best_weight = f"CKPT/svs_best_{args.label}.pth"
     ckpt_weight = f"CKPT/svs_{args.label}.pth"
 
-    train_set = SpectrogramDataset(args.train_folder, device=device, seed=None if world == 1 else 1234 + rank)
+    mr = bool(args.mr_stft)
+    mr_loss_fn = None
+    if mr:
+        from . import losses
+        mr_loss_fn = losses.MultiResolutionSTFTLoss(sample_rate=SAMPLE_RATE).to(device)
+    train_set = SpectrogramDataset(args.train_folder, device=device, seed=None if world == 1 else 1234 + rank,
+                                   with_phase=mr)
     valid_set = None
     if os.path.exists(args.valid_folder):
-        vs = SpectrogramDataset(args.valid_folder, device=device)
+        vs = SpectrogramDataset(args.valid_folder, device=device, with_phase=mr)
         valid_set = vs if len(vs) > 0 else None
     else:
         print(f"Warning: validation folder {args.valid_folder} not found, skipping validation.")
@@ -223,15 +262,25 @@ def main(argv=None):
                 torch.save(make_checkpoint(model, ep + 1), f"CKPT/svs_{args.label}_400.pth")
             print(f"\n[Info] Epoch {ep}: Learning rate manually changed to 5e-4!\n")
         loss_sum, n_it = 0.0, 0
-        for mix, voc in train_set.batches(args.batch_size, shuffle=True, rank=rank, world=world,
-                                          epoch_seed=base_seed + ep if world > 1 else None):
-            loss = training.train_step(model, mix, voc, two_term=True, loss_scale=alpha_L1)
-            loss_sum += alpha_L1 * float(loss[0])                    # train.py:303 (.item() per step)
+        for batch in train_set.batches(args.batch_size, shuffle=True, rank=rank, world=world,
+                                       epoch_seed=base_seed + ep if world > 1 else None):
+            if mr:                                                   # reference objective: autograd through the kernels
+                model.optim.zero_grad()
+                total, _, _ = full_objective(model, batch, mr_loss_fn)
+                total.backward()
+                if world > 1:
+                    for p_ in model.parameters():
+                        torch.distributed.all_reduce(p_.grad, op=torch.distributed.ReduceOp.AVG)
+                model.optim.step()
+                loss_sum += float(total)                             # train.py:303 (.item() per step)
+            else:
+                loss = training.train_step(model, batch[0], batch[1], two_term=True, loss_scale=alpha_L1)
+                loss_sum += alpha_L1 * float(loss[0])
             n_it += 1
         avg = loss_sum / max(n_it, 1)
         log_buffer.append(f"{avg}\n")
         if valid_set is not None and (ep + 1) % args.val_interval == 0:
-            val = validate(model, valid_set, args.batch_size, rank, world)
+            val = validate(model, valid_set, args.batch_size, rank, world, mr_loss_fn)
             log_buffer.append(f"Val {val}\n")
             print(f"\n[Epoch {ep + 1}] Train Loss: {avg:.4e} | Val Loss: {val:.4e}")
             if val < best_val:                                       # val is all-reduced: same decision on every rank

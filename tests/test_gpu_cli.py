@@ -119,9 +119,9 @@ def test_train_cli_one_epoch(tmp_path, monkeypatch):
     assert os.path.exists(str(tmp_path / "CKPT" / "svs_best_t.pth"))
     lines = open(str(tmp_path / "LOG" / "log_t.txt")).read().split("\n")
     assert any(l.startswith("Val ") for l in lines) and float(lines[0]) > 0      # loss_plot.py format
-    # resume from the checkpoint (train.py:216-237)
+    # resume from the checkpoint (train.py:216-237), this time on the L1-only fused CUDA-graph step
     train.main(["--train_folder", spec_dir, "--valid_folder", "missing", "--label", "t", "--epoch", "3",
-                "--batch_size", "4", "--load_path", str(tmp_path / "CKPT" / "svs_t.pth")])
+                "--batch_size", "4", "--load_path", str(tmp_path / "CKPT" / "svs_t.pth"), "--mr_stft", "0"])
     assert torch.load(str(tmp_path / "CKPT" / "svs_t.pth"), map_location="cpu")["epoch"] == 3
 
 

@@ -108,7 +108,7 @@ def test_fused_loss_kernel_matches_torch():
         ref = unet_oracle.l1_masked_loss(m, mix, voc, two_term=two)
         (gref,) = torch.autograd.grad(ref, m)
         loss, grad = training.masked_l1(m.detach(), mix, voc, two_term=two)
-        assert abs(float(loss[0]) - float(ref)) < 1e-6
+        assert abs(float(loss[0]) - float(ref.detach())) < 1e-6
         assert torch.allclose(grad, gref, atol=1e-9)
 
 
@@ -248,3 +248,36 @@ def test_graph_replayed_step_equals_the_eager_step(precision):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
     assert res[0][4] == res[1][4] == 3
+
+
+def test_mr_stft_objective_restatement():
+    # losses.py: specific_istft must agree with the hand-written iSTFT kernel on the same
+    # spectrogram, the MR-STFT loss is 0 for identical waveforms, positive otherwise, and the full objective of
+    # reference train.py:274-296 back-propagates through the sm_100a UNet
+    from svs_unet_pytorch_b200 import losses, spectral, synth, train as svs_train
+    mix, voc_wav, _ = synth.synth_song(12.0, seed=4)
+    batch = spectral.SongBatch.from_audio([mix[:768 * 127]])
+    mag, phase, _ = batch.stft()
+    assert mag.shape[0] == 128
+    ang = torch.atan2(phase[..., 1], phase[..., 0])
+    m4 = mag[:, 1:].T.reshape(1, 1, 512, 128).contiguous()
+    p4 = ang[:, 1:].T.reshape(1, 1, 512, 128).contiguous()
+    wav = losses.specific_istft(m4, p4)
+    mag0 = mag.clone()
+    mag0[:, 0] = 0                                                    # specific_istft re-inserts a ZERO DC row
+    ref, _ = batch.istft(mag0, phase)
+    assert wav.shape == (1, 1, 768 * 127)
+    assert (wav[0, 0] - ref).abs().max().item() < 2e-5
+    mr = losses.MultiResolutionSTFTLoss(sample_rate=8192).cuda()
+    assert float(mr(wav, wav)) == 0.0
+    assert float(mr(wav, 0.5 * wav)) > 0.1
+    net = _net(0.5, "tf32")
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 1, 512, 128, generator=g).cuda()
+    v = x * torch.rand(2, 1, 512, 128, generator=g).cuda()
+    ph = (torch.rand(2, 1, 512, 128, generator=g).cuda() - 0.5) * 6.0
+    total, l1, mrv = svs_train.full_objective(net, (x, v, ph, ph), mr)
+    total.backward()
+    assert torch.isfinite(total) and float(mrv.detach()) > 0 and float(l1.detach()) > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    assert float(net.conv3[0].weight.grad.abs().max()) > 0
