@@ -318,19 +318,18 @@ def run_ours(args):
     # ---- the tcgen05 conv family alone (conv2..deconv5) and per-layer device time ----
     g_tc = make_graphs(plan, 1, 10)
     ms_tc, _ = timed(replay_k(g_tc))
-    iv = _lib.PatchView(xs[0].data_ptr(), None, 512 * 128, 128, 1)
-    ov = _lib.PatchView(ys[0].data_ptr(), None, 512 * 128, 128, 1)
-    reps = 10
-    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(12)]
-           for _ in range(reps)]
-    for r in range(reps):
-        for li in range(12):
-            a, b = evs[r][li]
-            a.record()
-            plan.forward_views(iv, ov, None, BATCH, flags, li, li)
-            b.record()
-    torch.cuda.synchronize()
-    layer_ms = [sorted(evs[r][li][0].elapsed_time(evs[r][li][1]) for r in range(reps))[reps // 2] for li in range(12)]
+    # per-layer device time INSIDE the forward: CUDA graphs of the prefixes conv1..layer, rotating over the input pool
+    # like the headline; a layer's figure is the difference of consecutive prefixes (so the twelve add up to the step)
+    prefix_ms = []
+    for li in range(12):
+        if li == 11:
+            prefix_ms.append(ms_dev)
+            continue
+        g_pre = make_graphs(plan, 0, li)
+        t_pre, _ = timed(replay_k(g_pre), min_s=0.15)
+        prefix_ms.append(t_pre)
+        del g_pre
+    layer_ms = [prefix_ms[0]] + [prefix_ms[i] - prefix_ms[i - 1] for i in range(1, 12)]
     del g_tc
 
     # ---- full-song pipeline (BASELINE configs[2]/[3]): STFT -> UNet mask -> iSTFT, songs sharded by rank ----
@@ -545,6 +544,10 @@ def run_ours(args):
             "cudnn_baseline": cudnn,
             "train": train,
             "layer_us": {LAYER_NAMES[li]: round(layer_ms[li] * 1e3, 1) for li in range(12)},
+            "layer_us_note": "incremental device time of each layer inside the 64-patch forward: differences of CUDA-graph "
+                             "replays of the prefixes conv1..layer (same input rotation as `value`)",
+            "layer_frac_of_burst_peak": {LAYER_NAMES[li]: round(LAYER_MMAC[li] * 2e6 * BATCH / (max(layer_ms[li], 1e-6) * 1e-3)
+                                                                / 1e12 / peaks["bf16_burst"], 3) for li in range(12)},
         }
         if cudnn and "bf16_channels_last" in cudnn:
             line["vs_cudnn"] = {"bf16_vs_cudnn_bf16_channels_last": (BATCH / (ms_dev * 1e-3)) / cudnn["bf16_channels_last"]["patches_per_sec"],

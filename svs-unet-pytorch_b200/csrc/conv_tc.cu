@@ -390,7 +390,7 @@ static PFN_cuTensorMapEncodeTiled get_encode_fn() {
 }
 
 int encode_tensor_map(CUtensorMap* map, bool tf32, int rank, void* base, const cuuint64_t* dims,
-                      const cuuint64_t* strides_bytes, const cuuint32_t* box, int swz) {
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box, int swz, int l2_promotion) {
   PFN_cuTensorMapEncodeTiled fn = get_encode_fn();
   if (!fn) return fail(SVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -401,7 +401,10 @@ int encode_tensor_map(CUtensorMap* map, bool tf32, int rank, void* base, const c
                                 : swz == 12832 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base,
                   dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  l2_promotion >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                  : l2_promotion >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                  : l2_promotion >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SVS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
   return SVS_OK;
 }

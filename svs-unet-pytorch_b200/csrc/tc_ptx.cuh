@@ -136,7 +136,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
+// l2_promotion: bytes the L2 fetches around every TMA request (256 default; 0 / 64 / 128 for boxes whose rows are a
+// narrow window of a wider pixel, so that the unused neighbour bytes are not pulled from DRAM)
 int encode_tensor_map(CUtensorMap* map, bool fp32, int rank, void* base, const cuuint64_t* dims,
-                      const cuuint64_t* strides_bytes, const cuuint32_t* box, int swz);
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box, int swz, int l2_promotion = 256);
 
 }  // namespace svs

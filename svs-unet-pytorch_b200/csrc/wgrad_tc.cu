@@ -39,13 +39,23 @@
 namespace svs {
 
 constexpr int kWgThreads = 192;
-constexpr int kWgASlots = 2, kWgBSlots = 4;
-constexpr int kWgTapsPerPass = 13;
-constexpr int kWgN = 32;                               // channels of L per CTA
+constexpr int kWgASlots = 2;
 constexpr int kWgAChunkBytes = 128 * 128;              // [128 pixels][32 channels] fp32
 constexpr int kWgABytes = 4 * kWgAChunkBytes;
-constexpr int kWgBBytes = 128 * 128;                   // [128 pixels][32 channels] fp32
-constexpr size_t kWgSmemBytes = static_cast<size_t>(kWgASlots) * kWgABytes + kWgBSlots * kWgBBytes + 1024 + 256;
+// kN = channels of L per CTA (32 or 64).  512 TMEM columns hold 512 / kN - 3 accumulators of kN columns with room
+// to spare (13 for kN = 32, 7 for kN = 64), so the 25 taps take 2 or 4 passes over the CTA's pixel tiles; successive
+// passes overlap by one tap (pass p covers taps p (T-1) .. p (T-1) + T-1), which keeps every pass the same length.
+// The wide form needs half the MMAs per channel but re-loads S four times instead of twice; measured equal or slightly
+// slower at batch 64, so N = 32 is the default and N = 64 stays as an option (SVS_WGRAD_N64=1, parity-tested).
+template <int kN> struct WgCfg {
+  static constexpr int kTaps = kN == 32 ? 13 : 7;
+  static constexpr int kPasses = kN == 32 ? 2 : 4;
+  static constexpr int kBSlots = kN == 32 ? 4 : 3;
+  static constexpr int kBBytes = (kN / 32) * kWgAChunkBytes;      // kN / 32 chunks of [128 pixels][32 channels] fp32
+  static constexpr size_t kSmem = static_cast<size_t>(kWgASlots) * kWgABytes + kBSlots * kBBytes + 1024 + 256;
+  static_assert((kPasses - 1) * (kTaps - 1) + kTaps == 25, "passes must cover the 25 taps");
+  static_assert(kTaps * kN <= 512, "TMEM columns");
+};
 
 struct WgParams {
   int m_tiles, n_tiles, splits;          // work units (m tile, n tile) x pixel-tile splits
@@ -66,9 +76,12 @@ __device__ __forceinline__ uint64_t wg_desc(uint32_t addr, uint32_t lbo_bytes) {
          (static_cast<uint64_t>(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
+template <int kWgN>
 __global__ void __launch_bounds__(kWgThreads)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_l,
                 const __grid_constant__ WgParams p) {
+  constexpr int kWgTapsPerPass = WgCfg<kWgN>::kTaps, kWgPasses = WgCfg<kWgN>::kPasses, kWgBSlots = WgCfg<kWgN>::kBSlots;
+  constexpr int kWgBBytes = WgCfg<kWgN>::kBBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -110,8 +123,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constan
   if (warp == 0) {
     // ===== TMA producer =====
     int it_a = 0, it_b = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      const int tap0 = pass * (25 - kWgTapsPerPass);
+    for (int pass = 0; pass < kWgPasses; ++pass) {
+      const int tap0 = pass * (kWgTapsPerPass - 1);
       for (int i = 0; i < n_my; ++i, ++it_a) {
         const int tile = t_begin + i;
         const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, tb = tile / (p.ntw * p.nth);
@@ -135,8 +148,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constan
           mbar_wait(empty_b(sb), ((it_b / kWgBSlots) & 1) ^ 1);
           if (elect_one_sync()) {
             mbar_expect_tx(full_b(sb), kWgBBytes);
-            tma_load_5d(b_base + sb * kWgBBytes, &tmap_l, full_b(sb), pw * p.l_pitch + p.l_coff + nt * kWgN, tw * p.bw + dw,
-                        ph, th * p.bh + dh, tb * p.nb);
+            for (int c = 0; c < kWgN / 32; ++c)
+              tma_load_5d(b_base + sb * kWgBBytes + c * kWgAChunkBytes, &tmap_l, full_b(sb),
+                          pw * p.l_pitch + p.l_coff + nt * kWgN + c * 32, tw * p.bw + dw, ph, th * p.bh + dh, tb * p.nb);
           }
           __syncwarp();
         }
@@ -147,9 +161,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constan
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                (static_cast<uint32_t>(kWgN >> 3) << 17) | ((128u >> 4) << 24);
     int it_a = 0, it_b = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 1) {                                   // the epilogue has drained the accumulators of pass 0
-        mbar_wait(acc_empty, 0);
+    for (int pass = 0; pass < kWgPasses; ++pass) {
+      if (pass > 0) {                                    // the epilogue has drained the accumulators of the last pass
+        mbar_wait(acc_empty, (pass - 1) & 1);
         tc_fence_after();
       }
       for (int i = 0; i < n_my; ++i, ++it_a) {
@@ -165,7 +179,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constan
           dispatch_stage<0, kWgASlots * kWgBSlots>(sa * kWgBSlots + sb, [&](auto sc) {
             constexpr int SA = decltype(sc)::value / kWgBSlots, SB = decltype(sc)::value % kWgBSlots;
             const uint64_t da = wg_desc(smem_base + SA * kWgABytes, kWgAChunkBytes);
-            const uint64_t db = wg_desc(smem_base + kWgASlots * kWgABytes + SB * kWgBBytes, kWgBBytes);
+            const uint64_t db = wg_desc(smem_base + kWgASlots * kWgABytes + SB * kWgBBytes, kWgAChunkBytes);
             if (elect_one_sync()) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)       // K step j = pixel rows 8j .. 8j+7: +1024 B on both start addresses
@@ -191,28 +205,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constan
     const size_t tap_pitch = static_cast<size_t>(p.s_c) * p.l_c;
     float* dst0 = p.partial + (static_cast<size_t>(split) * 25 * p.s_c + m) * p.l_c + nt * kWgN;
     const int n_valid = min(kWgN, p.l_c - nt * kWgN);            // 32, or 16 for the 16-channel layers
-    for (int pass = 0; pass < 2; ++pass) {
-      const int tap0 = pass * (25 - kWgTapsPerPass);
-      mbar_wait(acc_full, pass);
+    for (int pass = 0; pass < kWgPasses; ++pass) {
+      const int tap0 = pass * (kWgTapsPerPass - 1);
+      mbar_wait(acc_full, pass & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < kWgTapsPerPass; ++t) {
-        uint32_t v[32];
-        if (n_my > 0) {
-          tmem_ld16(taddr + t * kWgN, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-          tmem_ld16(taddr + t * kWgN + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-          tmem_ld_wait();
-        } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = 0u;
-        }
-        if (m < p.s_c) {
-          float4* d4 = reinterpret_cast<float4*>(dst0 + (tap0 + t) * tap_pitch);
+        for (int h = 0; h < kWgN; h += 32) {
+          uint32_t v[32];
+          if (n_my > 0) {
+            tmem_ld16(taddr + t * kWgN + h, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_ld16(taddr + t * kWgN + h + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (4 * k < n_valid)
-              d4[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
-                                  __uint_as_float(v[4 * k + 3]));
+            for (int k = 0; k < 32; ++k) v[k] = 0u;
+          }
+          if (m < p.s_c) {
+            float4* d4 = reinterpret_cast<float4*>(dst0 + (tap0 + t) * tap_pitch + h);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (h + 4 * k < n_valid)
+                d4[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                                    __uint_as_float(v[4 * k + 3]));
+          }
         }
       }
       tc_fence_before();
@@ -233,8 +250,17 @@ __global__ void __launch_bounds__(256)
 wgrad_tc_finalize_kernel(const float* __restrict__ partial, int splits, int s_c, int l_c, float* __restrict__ grad_w) {
   const int total = 25 * s_c * l_c;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[static_cast<size_t>(k) * total + i];
+    // four independent chains keep four loads in flight; the combination order is fixed (deterministic)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {
+      s0 += partial[static_cast<size_t>(k) * total + i];
+      s1 += partial[static_cast<size_t>(k + 1) * total + i];
+      s2 += partial[static_cast<size_t>(k + 2) * total + i];
+      s3 += partial[static_cast<size_t>(k + 3) * total + i];
+    }
+    for (; k < splits; ++k) s0 += partial[static_cast<size_t>(k) * total + i];
+    const float s = (s0 + s1) + (s2 + s3);
     const int n = i % l_c, m = (i / l_c) % s_c, tap = i / (l_c * s_c);
     grad_w[(static_cast<size_t>(m) * l_c + n) * 25 + tap] = s;
   }
@@ -244,8 +270,16 @@ wgrad_tc_finalize_kernel(const float* __restrict__ partial, int splits, int s_c,
 // host
 struct WgGeom { int bw, bh, nb, ntw, nth, pix_tiles, m_tiles, n_tiles, splits; };
 
+static int wg_n(int l_c) {
+  // N = 64 (four passes) is parity-green but not faster: the kernel is bound by operand bytes into shared memory, and
+  // four passes re-load S twice as often as two (measured at batch 64: 4.0 vs 3.9 ms per training step) -> opt-in
+  static const bool wide = [] { const char* e = std::getenv("SVS_WGRAD_N64"); return e && e[0] == '1'; }();
+  return (l_c % 64 == 0 && wide) ? 64 : 32;
+}
+
 static WgGeom wg_geom(int gh, int gw, int batch, int s_c, int l_c) {
   WgGeom g{};
+  const int kWgN = wg_n(l_c);
   g.bw = gw < 16 ? gw : 16;
   g.bh = gh < 128 / g.bw ? gh : 128 / g.bw;
   g.nb = 128 / (g.bw * g.bh);
@@ -313,10 +347,16 @@ int wgrad_tc_launch(const float* S, int s_pitch, int s_coff, int s_c, const floa
   p.bw = g.bw; p.bh = g.bh; p.nb = g.nb;
   p.s_c = s_c; p.l_c = l_c; p.l_pitch = l_pitch; p.l_coff = l_coff; p.s_coff = s_coff;
   p.partial = partial;
-  SVS_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(kWgSmemBytes)));
   const int grid = g.m_tiles * g.n_tiles * g.splits;
-  wgrad_tc_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(ts, tl, p);
+  if (wg_n(l_c) == 64) {
+    SVS_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(WgCfg<64>::kSmem)));
+    wgrad_tc_kernel<64><<<grid, kWgThreads, WgCfg<64>::kSmem, st>>>(ts, tl, p);
+  } else {
+    SVS_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(WgCfg<32>::kSmem)));
+    wgrad_tc_kernel<32><<<grid, kWgThreads, WgCfg<32>::kSmem, st>>>(ts, tl, p);
+  }
   SVS_CHECK_LAUNCH("wgrad_tc_kernel");
   const int total = 25 * s_c * l_c;
   int blocks = (total + 255) / 256;

@@ -499,9 +499,10 @@ int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
   // slab row = 128 bytes of channels, or exactly the layer's own channel window when that is narrower (conv2, conv3:
   // the skip half of a concat pixel): the other half is then never fetched
   static const bool narrow_on = [] { const char* e = std::getenv("SVS_ZC_NARROW"); return !(e && e[0] == '0'); }();
+  static const bool narrow_conv2 = [] { const char* e = std::getenv("SVS_ZC_NARROW"); return e && e[0] == '2'; }();
   int row_bytes = 128;
   if (narrow_on && !g.transposed && g.cin * es < 128 && (g.cin * es == 32 || g.cin * es == 64) &&
-      (g.in_coff * es) % (g.cin * es) == 0 && li == 2)
+      (g.in_coff * es) % (g.cin * es) == 0 && (li == 2 || (li == 1 && narrow_conv2)))
     row_bytes = g.cin * es;          // conv3 only: conv2 is DRAM bound either way (32-byte sectors of 64-byte DRAM
                                      // atoms save nothing) and TMA issues ~5 cycles per slab row whatever its width,
                                      // so 32-byte rows were slower there (measured: 4,600 vs 3,750 cycles per tile)
@@ -624,7 +625,9 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
       strides[0] = ct * es; strides[1] = W * ct * es; strides[2] = W * ct * es; strides[3] = H * W * ct * es;
     }
     const cuuint32_t box[5] = {static_cast<cuuint32_t>(z.row_elems), kZcPw, 1, kZcPh, 1};
-    int rc = encode_tensor_map(&ta, tf32, 5, ws.buf[g.in_buf], dims, strides, box, z.row_bytes);
+    // narrow rows: do not let the L2 promote the request to the whole 128- / 256-byte pixel neighbourhood
+    int rc = encode_tensor_map(&ta, tf32, 5, ws.buf[g.in_buf], dims, strides, box, z.row_bytes,
+                               z.row_bytes < 128 ? (z.row_bytes >= 64 ? 64 : 0) : 256);
     if (rc != SVS_OK) return rc;
   }
   ZcParams p{};

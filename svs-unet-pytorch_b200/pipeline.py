@@ -158,22 +158,23 @@ class SongStreamer:
 class PatchStreamer:
     """Host-buffer entry point for patch batches: pinned host -> device -> UNet -> pinned host, with the
     H2D copy of batch i+1 and the D2H copy of batch i-1 overlapping the kernels of batch i (three
-    streams, double-buffered device staging).  Mirrors what reference inference.py:97-110 does one
+    streams, n_buf-deep device staging).  Mirrors what reference inference.py:97-110 does one
     patch at a time with a synchronous .to(device) / .cpu() pair."""
 
-    def __init__(self, model, batch: int = 64, vocal_solo: bool | None = None):
+    def __init__(self, model, batch: int = 64, vocal_solo: bool | None = None, n_buf: int = 4):
         self.model = model
         self.batch = batch
         self.flags = 0 if vocal_solo is None else (_lib.FLAG_APPLY_MASK | (0 if vocal_solo else _lib.FLAG_INVERT))
         dev = next(model.parameters()).device
         self.dev = dev
-        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.n_buf = max(2, int(n_buf))                                 # staging depth: 2 leaves the copy engines idle
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))   # whenever a step jitters
         shape = (batch, 1, 512, 128)
-        self.d_in = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
-        self.d_out = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(2)]
-        self.ev_in = [torch.cuda.Event() for _ in range(2)]
-        self.ev_cmp = [torch.cuda.Event() for _ in range(2)]
-        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.d_in = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(self.n_buf)]
+        self.d_out = [torch.empty(shape, dtype=torch.float32, device=dev) for _ in range(self.n_buf)]
+        self.ev_in = [torch.cuda.Event() for _ in range(self.n_buf)]
+        self.ev_cmp = [torch.cuda.Event() for _ in range(self.n_buf)]
+        self.ev_out = [torch.cuda.Event() for _ in range(self.n_buf)]
         self.plan = model.plan()
 
     @torch.no_grad()
@@ -181,19 +182,20 @@ class PatchStreamer:
         """host_in / host_out: sequences of pinned float32 tensors (batch,1,512,128).  Returns after the
         last result has landed in host memory."""
         n = len(host_in)
+        nb = self.n_buf
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
         for i in range(n):
-            k = i & 1
+            k = i % nb
             with torch.cuda.stream(self.s_in):
-                if i >= 2:
+                if i >= nb:
                     self.s_in.wait_event(self.ev_cmp[k])              # staging buffer k was consumed
                 self.d_in[k].copy_(host_in[i], non_blocking=True)
                 self.ev_in[k].record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(self.ev_in[k])
-                if i >= 2:
+                if i >= nb:
                     self.s_cmp.wait_event(self.ev_out[k])             # result buffer k was drained
                 self.plan.forward_dense(self.d_in[k], self.flags, self.d_out[k])
                 self.ev_cmp[k].record(self.s_cmp)

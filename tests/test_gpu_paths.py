@@ -57,3 +57,29 @@ def test_kernel_variant_matches_oracle(name, tmp_path):
     env = dict(os.environ, SVS_ROOT=ROOT, **VARIANTS[name])
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_wide_wgrad_variant_matches_float64(tmp_path):
+    # SVS_WGRAD_N64=1: the four-pass N = 64 form of wgrad_tc_kernel (selected once per process)
+    script = tmp_path / "w.py"
+    script.write_text("""
+import os, sys, torch
+sys.path.insert(0, os.environ["SVS_ROOT"])
+from svs_unet_pytorch_b200 import _lib
+def tf32(x): return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+g = torch.Generator().manual_seed(1)
+for (b, gh, gw, cs, cl) in [(3, 16, 8, 64, 64), (8, 8, 2, 256, 128), (2, 32, 16, 32, 16)]:
+    S = tf32(torch.randn(b, gh, gw, cs, generator=g)); L = tf32(torch.randn(b, 2 * gh, 2 * gw, cl, generator=g))
+    Lp = torch.nn.functional.pad(L.double(), (0, 0, 2, 2, 2, 2))
+    ref = torch.zeros(cs, cl, 5, 5, dtype=torch.float64)
+    for kh in range(5):
+        for kw in range(5):
+            ref[:, :, kh, kw] = torch.einsum("byxm,byxn->mn", S.double(), Lp[:, kh:kh + 2 * gh:2, kw:kw + 2 * gw:2, :])
+    got = _lib.conv_wgrad_tf32(S.cuda(), L.cuda()).cpu().double()
+    err = float((got - ref).norm() / ref.norm())
+    assert err <= 2e-6, err
+print("ok")
+""")
+    env = dict(os.environ, SVS_ROOT=ROOT, SVS_WGRAD_N64="1")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

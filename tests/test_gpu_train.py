@@ -213,7 +213,8 @@ def test_conv_wgrad_tf32_op_matches_float64():
 
     g = torch.Generator().manual_seed(1)
     for (b, gh, gw, cs, cl, scoff, lcoff) in [(3, 16, 8, 64, 32, 0, 0), (8, 8, 2, 256, 32, 0, 0), (2, 32, 16, 32, 16, 0, 16),
-                                              (5, 16, 4, 160, 48, 0, 0), (2, 64, 16, 32, 16, 0, 0)]:
+                                              (5, 16, 4, 160, 48, 0, 0), (2, 64, 16, 32, 16, 0, 0),
+                                              (3, 16, 8, 64, 64, 0, 0), (8, 8, 2, 256, 128, 0, 0), (9, 16, 4, 128, 64, 0, 64)]:
         S = tf32(torch.randn(b, gh, gw, cs, generator=g))
         L = tf32(torch.randn(b, 2 * gh, 2 * gw, cl + lcoff, generator=g))
         Lp = torch.nn.functional.pad(L[..., lcoff:].double(), (0, 0, 2, 2, 2, 2))
