@@ -272,7 +272,7 @@ def main(argv=None):
                     for p_ in model.parameters():
                         torch.distributed.all_reduce(p_.grad, op=torch.distributed.ReduceOp.AVG)
                 model.optim.step()
-                loss_sum += float(total)                             # train.py:303 (.item() per step)
+                loss_sum += float(total.detach())                    # train.py:303 (.item() per step)
             else:
                 loss = training.train_step(model, batch[0], batch[1], two_term=True, loss_scale=alpha_L1)
                 loss_sum += alpha_L1 * float(loss[0])
