@@ -114,7 +114,8 @@ int svs_spec_normalize(float* mag, const int64_t* frame_off, const float* norm, 
  * Replaces `librosa.istft(mag * phase, win_length=1024, hop_length=768)` at reference data.py:159:
  * complex recombine, inverse real FFT, Hann window, deterministic gather-form overlap-add (no
  * atomics), division by the window-sum-of-squares envelope, trim n_fft/2 on both ends.
- *   wave         float32; song s occupies wave[wave_off[s] .. wave_off[s] + 768*(T_s-1))
+ *   wave         float32, 16-byte aligned; song s occupies wave[wave_off[s] .. wave_off[s] + 768*(T_s-1)), wave_off[s]
+ *                a multiple of 4 (back-to-back songs: multiples of 768)
  *   song_peak    float32 [n_songs] max |y| per song (reference data.py:162); may be NULL
  */
 int svs_istft_ola(const float* mag, const float* phase, const int64_t* frame_off,

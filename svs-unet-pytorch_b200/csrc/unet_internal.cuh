@@ -149,6 +149,7 @@ struct ZcLayer {
   void* d_weights = nullptr;
   CUtensorMap tmap_b;
   CUtensorMap tmap_b_half;           // box of n_total / 2 rows: one CTA's share of a multicast weight chunk
+  CUtensorMap tmap_b_quarter;        // box of n_total / 4 rows: one sub-pixel phase block of a merged deconv chunk
 };
 
 }  // namespace svs

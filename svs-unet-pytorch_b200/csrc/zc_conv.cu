@@ -126,11 +126,19 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
 // the streamed weight chunks: each CTA issues one half of every chunk as a multicast TMA load that lands in both
 // CTAs.  A slot may be refilled only when BOTH CTAs have consumed it: the MMA warp's commit arrives on the slot's
 // `empty` barrier of both CTAs (count 2).  Parity-green but not faster (see zc_launch_layer), so off by default.
-template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1>
+// kTrim (phase-merged deconvs with streamed weights): a tap (dy, dx) only reaches the sub-pixel phases whose kernel
+// index kh = py + 2 - 2 dy, kw = px + 2 - 2 dx exists, i.e. py = 0 alone when dy = -1 and px = 0 alone when dx = -1.
+// With the accumulator columns ordered [(0,0) (0,1) (1,0) (1,1)] x Cout, the nine taps need 1, 2, 2 (as two
+// single-phase MMAs) or 4 phase blocks instead of 4 each: 25 blocks of weights instead of 36 are fetched (the layers
+// are bound by bytes into shared memory) and 25 / 36 of the MMA columns are issued.  The tile's very first tap still
+// runs over all four blocks (its unused ones hold zero weights) so that one instruction initialises every column.
+template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1,
+          bool kTrim = false>
 __global__ void __launch_bounds__(kZcThreads)
 zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ZcParams p) {
   static_assert(kCluster == 1 || kCluster == 2, "CTA pairs only");
+  static_assert(!kTrim || (kCluster == 1 && kRow == 128 && Taps::kStatic && kBlockN % 64 == 0), "trimmed form");
   constexpr uint16_t kMask = (1u << kCluster) - 1u;
   constexpr int kBBytes = kBlockN * kRow;
   constexpr int kZcATx = zc_a_tx<kRow>(), kZcASlot = zc_a_slot<kRow>();
@@ -218,10 +226,20 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const int bs = jb % kBSlots;
               mbar_wait(empty_b(bs), ((jb / kBSlots) & 1) ^ 1);
               if (elect_one_sync()) {
-                mbar_expect_tx(full_b(bs), kBBytes);
-                if constexpr (kCluster == 1) {
+                if constexpr (kTrim) {               // tmap_b's box is one phase block (kBlockN / 4 rows)
+                  const bool full = next_tap == 0;
+                  const int pyn = (full || p.sch.tap_dy[next_tap] >= 0) ? 2 : 1;
+                  const int pxn = (full || p.sch.tap_dx[next_tap] >= 0) ? 2 : 1;
+                  mbar_expect_tx(full_b(bs), static_cast<uint32_t>(pyn * pxn) * (kBBytes / 4));
+                  for (int py = 0; py < pyn; ++py)
+                    for (int px = 0; px < pxn; ++px)
+                      tma_load_2d(b_base + bs * kBBytes + (2 * py + px) * (kBBytes / 4), &tmap_b, full_b(bs),
+                                  next_tap * p.row_elems, (2 * py + px) * (kBlockN / 4));
+                } else if constexpr (kCluster == 1) {
+                  mbar_expect_tx(full_b(bs), kBBytes);
                   tma_load_2d(b_base + bs * kBBytes, &tmap_b, full_b(bs), next_tap * p.row_elems, 0);
-                } else {                          // my half of the rows, into both CTAs (tmap_b's box is kBlockN / 2 rows)
+                } else {
+                  mbar_expect_tx(full_b(bs), kBBytes);     // my half of the rows, into both CTAs (box = kBlockN / 2 rows)
                   const int half = static_cast<int>(zc_cluster_rank());
                   tma_load_2d_mcast(b_base + bs * kBBytes + half * (kBBytes / 2), &tmap_b, full_b(bs), next_tap * p.row_elems,
                                     half * (kBlockN / 2), kMask);
@@ -277,12 +295,34 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const uint64_t db = make_smem_desc<kRow>(b_addr);
                 const uint32_t a_off16 = static_cast<uint32_t>(((dy + 1) * kZcPw + (dx + 1)) * kRow) >> 4;
                 if (elect_one_sync()) {
+                  if constexpr (kTrim) {
+                    constexpr int C = kBlockN / 4;
+                    constexpr uint32_t idesc1 = make_idesc<kTf32, C>(), idesc2 = make_idesc<kTf32, 2 * C>();
+                    constexpr uint32_t blk16 = static_cast<uint32_t>(C * kRow) >> 4;     // one phase block of B rows
+                    const bool full = (s == 0 && dy == -1 && dx == -1) || (dy >= 0 && dx >= 0);
+#pragma unroll
+                    for (int k = 0; k < kKSteps; ++k) {
+                      const uint64_t dak = da0 + a_off16 + 2u * k, dbk = db + 2u * k;
+                      if (full) {
+                        umma<kTf32>(tmem_d, dak, dbk, idesc, first_mma ? 0u : 1u);
+                      } else if (dy == -1 && dx == -1) {                // phase (0,0)
+                        umma<kTf32>(tmem_d, dak, dbk, idesc1, 1u);
+                      } else if (dy == -1) {                            // phases (0,0) (0,1)
+                        umma<kTf32>(tmem_d, dak, dbk, idesc2, 1u);
+                      } else {                                          // dx == -1: phases (0,0) and (1,0)
+                        umma<kTf32>(tmem_d, dak, dbk, idesc1, 1u);
+                        umma<kTf32>(tmem_d + 2 * C, dak, dbk + 2u * blk16, idesc1, 1u);
+                      }
+                      first_mma = false;
+                    }
+                  } else {
 #pragma unroll
                   for (int k = 0; k < kKSteps; ++k) {
                     if (kmask & (1 << k)) {
                       umma<kTf32>(tmem_d, da0 + a_off16 + 2u * k, db + 2u * k, idesc, first_mma ? 0u : 1u);
                       first_mma = false;
                     }
+                  }
                   }
                   if (!p.resident) {
                     if constexpr (kCluster == 1) umma_commit(empty_b(bs));
@@ -565,6 +605,9 @@ int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
   const cuuint32_t box_half[2] = {static_cast<cuuint32_t>(row), static_cast<cuuint32_t>(n_total / 2)};
   rc = encode_tensor_map(&z.tmap_b_half, tf32, 2, z.d_weights, dims, strides, box_half, row_bytes);
   if (rc != SVS_OK) return rc;
+  const cuuint32_t box_q[2] = {static_cast<cuuint32_t>(row), static_cast<cuuint32_t>(n_total / 4)};
+  rc = encode_tensor_map(&z.tmap_b_quarter, tf32, 2, z.d_weights, dims, strides, box_q, row_bytes);
+  if (rc != SVS_OK) return rc;
   z.enabled = true;
   return SVS_OK;
 }
@@ -577,9 +620,10 @@ void zc_free_layers(svs_unet_plan* plan) {
   }
 }
 
-template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1>
+template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1,
+          bool kTrim = false>
 static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcParams& p, cudaStream_t st) {
-  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps, kRow, kCluster>;
+  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps, kRow, kCluster, kTrim>;
   constexpr size_t smem = zc_smem_bytes<kBlockN, kASlots, kBSlots, kRow>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
   SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -668,6 +712,24 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   // reduce; only splitting B across the pair (cta_group::2) or two M tiles per weight pass would.
   static const bool mcast_on = [] { const char* e = std::getenv("SVS_ZC_MCAST"); return e && e[0] == '1'; }();
   const bool pair = mcast_on && !z.resident && p.m_tiles % 2 == 0 && p.m_tiles >= 2;
+  // phase-trimmed merged deconvs (streamed weights): see zc_conv_kernel.  OFF by default — measured at batch 64: bf16
+  // 222.8 vs 221.6 us, TF32 487.7 vs 439.3 us per forward.  Trimming removes weight bytes and MMA columns in the same
+  // proportion, and the streamed-weight ring is LATENCY bound (bytes in flight per SM are capped by shared memory:
+  // ring bytes / L2 latency ~ 55 B/clk), so the ratio that matters — MMA work per streamed byte — does not improve,
+  // while the quarter-chunk loads and N = Cout instructions add requests.
+  static const bool trim_on = [] { const char* e = std::getenv("SVS_ZC_TRIM"); return e && e[0] == '1'; }();
+  const bool trim = trim_on && g.transposed && !z.resident && !pair && n % 64 == 0;
+#define SVS_ZC_TRIMMED(TF, LI, N, AS, BS, TAPS)                                                      \
+  if (trim && tf32 == TF && li == LI && n == N && z.sch.n_slabs == TAPS::kSlabs) {                    \
+    if constexpr (TF) return zc_launch_t<float, true, N, AS, BS, TAPS, 128, 1, true>(ta, z.tmap_b_quarter, p, st);          \
+    else return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS, 128, 1, true>(ta, z.tmap_b_quarter, p, st);              \
+  }
+  SVS_ZC_TRIMMED(false, 8, 256, 3, 4, ZcDeconvTaps<4>)
+  SVS_ZC_TRIMMED(false, 9, 128, 2, 3, ZcDeconvTaps<2>)
+  SVS_ZC_TRIMMED(true, 8, 256, 3, 4, ZcDeconvTaps<8>)
+  SVS_ZC_TRIMMED(true, 9, 128, 4, 4, ZcDeconvTaps<4>)
+  SVS_ZC_TRIMMED(true, 10, 64, 3, 6, ZcDeconvTaps<2>)
+#undef SVS_ZC_TRIMMED
 #define SVS_ZC_STATIC(TF, LI, N, AS, BS, RES, TAPS)                                                 \
   if (tf32 == TF && li == LI && n == N && z.resident == RES && z.sch.n_slabs == TAPS::kSlabs) {       \
     if constexpr (!RES) {                                                                             \

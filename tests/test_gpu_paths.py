@@ -46,6 +46,7 @@ VARIANTS = {
     "wide_tiles_large_batch": {"SVS_TEST_BATCH": "160"},                # conv5 / conv6 / deconv1 on 128 x 256 tiles
     "narrow_tiles_large_batch": {"SVS_TEST_BATCH": "160", "SVS_TC_NO_WIDE": "1"},
     "full_width_slab_rows": {"SVS_ZC_NARROW": "0"},
+    "phase_trimmed_merged_deconv": {"SVS_ZC_TRIM": "1"},                # deconv3 / deconv4 taps only over the phase blocks they reach
     "weight_multicast_pairs": {"SVS_ZC_MCAST": "1"},                    # CTA pairs share streamed weight chunks (TMA multicast)                     # conv2 / conv3 on 128-byte rows (both concat halves)
 }
 
