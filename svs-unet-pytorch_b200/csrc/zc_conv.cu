@@ -741,6 +741,14 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     if constexpr (TF) return zc_launch_t<float, true, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);          \
     else return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS>(ta, z.tmap_b, p, st);              \
   }
+  // experiment (SVS_ZC_RING=1): deeper weight rings at the expense of slab slots — the streamed-weight ring is latency
+  // bound, so more bytes in flight should raise throughput
+  static const bool deep_ring = [] { const char* e = std::getenv("SVS_ZC_RING"); return e && e[0] == '1'; }();
+  if (deep_ring) {
+    SVS_ZC_STATIC(false, 3, 128, 3, 9, false, ZcConvParityTaps<0xF>)      // conv4: 72 KB slabs + 144 KB weights
+    SVS_ZC_STATIC(false, 8, 256, 2, 5, false, ZcDeconvTaps<4>)            // deconv3: 48 KB + 160 KB
+    SVS_ZC_STATIC(false, 9, 128, 3, 9, false, ZcDeconvTaps<2>)            // deconv4: one CTA / SM, 72 KB + 144 KB
+  }
   SVS_ZC_STATIC(false, 1, 32, 2, 15, true, ZcConv2Taps)       // 2 CTAs / SM: one CTA's epilogue hides the other's loads
   SVS_ZC_STATIC(false, 2, 64, 3, 4, false, ZcConvParityTaps<0xC>)
   SVS_ZC_STATIC(false, 3, 128, 5, 6, false, ZcConvParityTaps<0xF>)
