@@ -132,20 +132,26 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
 // single-phase MMAs) or 4 phase blocks instead of 4 each: 25 blocks of weights instead of 36 are fetched (the layers
 // are bound by bytes into shared memory) and 25 / 36 of the MMA columns are issued.  The tile's very first tap still
 // runs over all four blocks (its unused ones hold zero weights) so that one instruction initialises every column.
+// kDual: the CTA works on TWO neighbouring M tiles at once (two accumulators per TMEM stage, a slab slot holds both
+// tiles' halo slabs) and every streamed weight chunk feeds both: the layer is bound by bytes streamed into the SM, and
+// this halves the weight bytes per MMA without a cluster.  N <= 128 (4 x N TMEM columns).
 template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1,
-          bool kTrim = false>
+          bool kTrim = false, bool kDual = false>
 __global__ void __launch_bounds__(kZcThreads)
 zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ZcParams p) {
   static_assert(kCluster == 1 || kCluster == 2, "CTA pairs only");
   static_assert(!kTrim || (kCluster == 1 && kRow == 128 && Taps::kStatic && kBlockN % 64 == 0), "trimmed form");
+  static_assert(!kDual || (kCluster == 1 && !kTrim && Taps::kStatic && kBlockN <= 128), "dual-tile form");
+  constexpr int kTiles = kDual ? 2 : 1;
   constexpr uint16_t kMask = (1u << kCluster) - 1u;
   constexpr int kBBytes = kBlockN * kRow;
-  constexpr int kZcATx = zc_a_tx<kRow>(), kZcASlot = zc_a_slot<kRow>();
+  constexpr int kZcATx = kTiles * zc_a_tx<kRow>(), kZcASlot = kTiles * zc_a_slot<kRow>(), kZcATile = zc_a_slot<kRow>();
   constexpr int kKSteps = kRow / 32;                              // UMMA K = 32 bytes
   constexpr uint64_t kLayout = kRow == 128 ? 2 : (kRow == 64 ? 4 : 6);   // UMMA layout type of the swizzle span
   constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;
-  constexpr int kTmemCols = 2 * kAccCols;
+  constexpr int kStageCols = kTiles * kAccCols;                   // accumulator columns of one TMEM stage
+  constexpr int kTmemCols = 2 * kStageCols;
   constexpr int kNBar = 2 * kBSlots + 2 * kASlots + 4;
 
   extern __shared__ uint8_t smem_raw[];
@@ -169,7 +175,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = p.dbg ? p.dbg + 64 * blockIdx.x : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
-  const int total_tiles = p.m_tiles;                  // kBlockN covers all of N
+  const int total_tiles = p.m_tiles / kTiles;         // work units (kBlockN covers all of N; dual: tile pairs)
   const int n_slabs = p.sch.n_slabs, n_taps = p.sch.n_taps;
 
   if (threadIdx.x == 0) {
@@ -202,14 +208,18 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       pdl_wait();                                 // activations of the previous layer from here on
       // slab jobs are numbered across tiles; the slab of job j+1 is requested BEFORE the weight chunks
       // of job j so the halo loads run one slab ahead of the MMAs
-      auto issue_a = [&](int ja, int tile, int s) {
+      auto issue_a = [&](int ja, int unit, int s) {
         const int slot = ja % kASlots;
-        const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, tb = tile / (p.ntw * p.nth);
         mbar_wait(empty_a(slot), ((ja / kASlots) & 1) ^ 1);
         if (elect_one_sync()) {
           mbar_expect_tx(full_a(slot), kZcATx);
-          tma_load_5d(smem_base + slot * kZcASlot, &tmap_a, full_a(slot), p.sch.slab_c[s], tw * kZcBw - 1,
-                      p.sch.slab_ph[s], th * kZcBh - 1, tb);
+#pragma unroll
+          for (int u = 0; u < kTiles; ++u) {
+            const int tile = unit * kTiles + u;
+            const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, tb = tile / (p.ntw * p.nth);
+            tma_load_5d(smem_base + slot * kZcASlot + u * kZcATile, &tmap_a, full_a(slot), p.sch.slab_c[s], tw * kZcBw - 1,
+                        p.sch.slab_ph[s], th * kZcBh - 1, tb);
+          }
         }
         __syncwarp();
         if (dbg && ja < 8 && lane == 0) dbg[8 + ja] = clock64();
@@ -262,7 +272,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int as = t & 1;
         mbar_wait(tmem_empty(as), ((t >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * kAccCols;
+        const uint32_t tmem_d = tmem_base + as * kStageCols;
         if constexpr (Taps::kStatic) {
           // ---- straight-line issue: slabs, shifts and k-steps unrolled at compile time ----
           bool first_mma = true;
@@ -320,6 +330,9 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   for (int k = 0; k < kKSteps; ++k) {
                     if (kmask & (1 << k)) {
                       umma<kTf32>(tmem_d, da0 + a_off16 + 2u * k, db + 2u * k, idesc, first_mma ? 0u : 1u);
+                      if constexpr (kDual)     // the second tile's slab sits kZcATile bytes further in the same slot
+                        umma<kTf32>(tmem_d + kAccCols, da0 + (static_cast<uint32_t>(kZcATile) >> 4) + a_off16 + 2u * k,
+                                    db + 2u * k, idesc, first_mma ? 0u : 1u);
                       first_mma = false;
                     }
                   }
@@ -401,14 +414,17 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const float slope = p.act == ACT_LEAKY ? 0.2f : 0.0f;
     const int cp_log2 = 31 - __clz(p.cout_phase), cp_mask = p.cout_phase - 1;   // channels per phase: a power of two
     const uint32_t out_pitch = p.out_pitch, out_coff = p.out_coff;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-      const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, b = tile / (p.ntw * p.nth);
-      const int gx = tw * kZcBw + ix, gy = th * kZcBh + iy;
+    for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++t) {
       const int as = t & 1;
       mbar_wait(tmem_full(as), (t >> 1) & 1);
       if (dbg && t < 8 && threadIdx.x == 64) dbg[32 + t] = clock64();
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kAccCols;
+#pragma unroll 1
+      for (int u = 0; u < kTiles; ++u) {
+      const int tile = unit * kTiles + u;
+      const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, b = tile / (p.ntw * p.nth);
+      const int gx = tw * kZcBw + ix, gy = th * kZcBh + iy;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kStageCols + u * kAccCols;
       constexpr int kStep = kBlockN >= 32 ? 32 : 16;
       // The epilogue of tile t runs under the MMAs of tile t+1 with ONE warp per scheduler, so it is bound by
       // dependent-issue latency: keep it short (branch-free activation, shifts, 32-bit offsets) or it, not the
@@ -444,6 +460,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           zc_store16(dst, f);
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -621,19 +638,20 @@ void zc_free_layers(svs_unet_plan* plan) {
 }
 
 template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1,
-          bool kTrim = false>
+          bool kTrim = false, bool kDual = false>
 static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcParams& p, cudaStream_t st) {
-  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps, kRow, kCluster, kTrim>;
-  constexpr size_t smem = zc_smem_bytes<kBlockN, kASlots, kBSlots, kRow>();
+  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps, kRow, kCluster, kTrim, kDual>;
+  constexpr int kTiles = kDual ? 2 : 1;
+  constexpr size_t smem = zc_smem_bytes<kBlockN, kTiles * kASlots, kBSlots, kRow>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
   SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
-  if (per_sm > 512 / (2 * kAccCols)) per_sm = 512 / (2 * kAccCols);
+  if (per_sm > 512 / (2 * kTiles * kAccCols)) per_sm = 512 / (2 * kTiles * kAccCols);
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
-  if (grid > p.m_tiles) grid = p.m_tiles;
+  if (grid > p.m_tiles / kTiles) grid = p.m_tiles / kTiles;
   if constexpr (kCluster == 1) {
     SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, ta, tb, p));
   } else {
@@ -749,6 +767,19 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     SVS_ZC_STATIC(false, 8, 256, 2, 5, false, ZcDeconvTaps<4>)            // deconv3: 48 KB + 160 KB
     SVS_ZC_STATIC(false, 9, 128, 3, 9, false, ZcDeconvTaps<2>)            // deconv4: one CTA / SM, 72 KB + 144 KB
   }
+  // two M tiles per weight pass (kDual): halves the streamed weight bytes per MMA.  Needs an even tile count and
+  // enough tile pairs to fill the GPU (one CTA per SM: the two double-buffered accumulators take all of TMEM).
+  static const int dual_mode = [] { const char* e = std::getenv("SVS_ZC_DUAL"); return e ? std::atoi(e) : 0; }();
+  const bool dual = dual_mode != 0 && !z.resident && !pair && p.m_tiles % 2 == 0 && p.m_tiles >= 2 * num_sms();
+#define SVS_ZC_DUAL(TF, LI, N, AS, BS, TAPS)                                                        \
+  if (dual && tf32 == TF && li == LI && n == N && z.sch.n_slabs == TAPS::kSlabs) {                    \
+    if constexpr (TF) return zc_launch_t<float, true, N, AS, BS, TAPS, 128, 1, false, true>(ta, z.tmap_b, p, st);          \
+    else return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS, 128, 1, false, true>(ta, z.tmap_b, p, st);              \
+  }
+  SVS_ZC_DUAL(false, 9, 128, 2, 7, ZcDeconvTaps<2>)           // deconv4: 92 KB of slabs + 112 KB weight ring
+  SVS_ZC_DUAL(false, 3, 128, 2, 7, ZcConvParityTaps<0xF>)     // conv4 (large batches only)
+  SVS_ZC_DUAL(true, 9, 128, 2, 7, ZcDeconvTaps<4>)
+#undef SVS_ZC_DUAL
   SVS_ZC_STATIC(false, 1, 32, 2, 15, true, ZcConv2Taps)       // 2 CTAs / SM: one CTA's epilogue hides the other's loads
   SVS_ZC_STATIC(false, 2, 64, 3, 4, false, ZcConvParityTaps<0xC>)
   SVS_ZC_STATIC(false, 3, 128, 5, 6, false, ZcConvParityTaps<0xF>)
