@@ -509,7 +509,7 @@ def run_ours(args):
                        "timed_region": f">= {MIN_REGION_S} s per measurement: the K-step loop is repeated back to back"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": step_bytes,
                     "d2h_bytes_per_step": step_bytes, "ms_per_step": ms_e2e, "timed_steps": n_e2e,
-                    "api": "pipeline.PatchStreamer.run (pinned host -> H2D -> svs_unet_forward -> D2H, 3 streams)",
+                    "api": "pipeline.PatchStreamer.run -> svs_patch_stream_run (pinned host -> H2D -> svs_unet_forward -> D2H, 3 streams, native loop)",
                     "frac_of_pcie": ms_copy / ms_e2e},
             "pcie": {"copy_only_ms_per_step": ms_copy, "gbs_per_rank_both_directions": copy_gbs,
                      "ceiling_patches_per_sec": BATCH * world / (ms_copy * 1e-3),

@@ -212,6 +212,24 @@ int svs_unet_read_activation(const svs_unet_plan* plan, int layer, int batch, co
 /* Number of kernel launches svs_unet_forward enqueues for this plan/batch (bench bookkeeping). */
 int svs_unet_launch_count(const svs_unet_plan* plan, int batch);
 
+/* ------------------------------------------------------------------ host-buffer patch batches
+ * Replaces the per-patch `.to(device)` -> model -> `.cpu()` round trip of reference inference.py:97-110 for callers
+ * whose patches live in (pinned) HOST memory.  Step i uploads host_in[i] (batch x 512 x 128 float32, dense) into
+ * device staging slot i % n_slots on stream_h2d, runs svs_unet_forward on stream_compute and downloads the result
+ * into host_out[i] on stream_d2h; batch i+1's upload and batch i-1's download overlap batch i's kernels, ordered by
+ * events the stream object owns.  Everything is enqueued; the call does not synchronise (wait on stream_d2h).
+ *   host_in / host_out   HOST arrays of n_steps host pointers (page-locked for the copies to be asynchronous)
+ *   dev_in / dev_out     HOST arrays of n_slots device pointers, batch*512*128 floats each
+ *   workspace            one device workspace of svs_unet_workspace_bytes(plan, batch) (forwards are serialised)
+ */
+typedef struct svs_patch_stream svs_patch_stream;   /* opaque: 3 x n_slots events */
+int svs_patch_stream_create(int n_slots, svs_patch_stream** out);
+int svs_patch_stream_destroy(svs_patch_stream* ps);
+int svs_patch_stream_run(svs_patch_stream* ps, const svs_unet_plan* plan, const float* const* host_in,
+                         float* const* host_out, int n_steps, int batch, int flags, float* const* dev_in,
+                         float* const* dev_out, void* workspace, size_t workspace_bytes, void* stream_h2d,
+                         void* stream_compute, void* stream_d2h);
+
 /* ------------------------------------------------------------------ training step (T1)
  * Replaces the autograd graph of reference train.py:274-299 (mask = model(mix) in train mode, L1 loss,
  * loss.backward()): train-mode forward (batch-statistic BatchNorm + running-stat update with momentum

@@ -75,6 +75,11 @@ _SIGNATURES = [
     ("svs_debug_set_trace", c_int, [c_void_p, c_int]),
     ("svs_unet_read_activation", c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     ("svs_unet_launch_count", c_int, [c_void_p, c_int]),
+    ("svs_patch_stream_create", c_int, [c_int, POINTER(c_void_p)]),
+    ("svs_patch_stream_destroy", c_int, [c_void_p]),
+    ("svs_patch_stream_run", c_int, [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int,
+                                     POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_size_t, c_void_p, c_void_p,
+                                     c_void_p]),
     ("svs_unet_train_plan_create", c_int, [c_void_p, POINTER(c_void_p)]),
     ("svs_unet_train_plan_destroy", c_int, [c_void_p]),
     ("svs_unet_train_workspace_bytes", c_size_t, [c_int]),

@@ -123,6 +123,16 @@ def test_host_streamer_matches_direct_forward():
     for a, b in zip(hin, hout):
         ref = net.separate(a.cuda(), vocal_solo=True).cpu()
         assert torch.equal(b, ref)
+    # a second run on the same streamer (slot events recorded by the first), more steps than staging slots, inputs
+    # in another order
+    hout2 = [torch.zeros(4, 1, 512, 128).pin_memory() for _ in range(11)]
+    order = [3, 1, 4, 0, 2, 2, 0, 4, 1, 3, 0]
+    st.run([hin[i] for i in order], hout2)
+    torch.cuda.synchronize()
+    for i, b in zip(order, hout2):
+        assert torch.equal(b, hout[i])
+    with pytest.raises(Exception):
+        st.run([torch.rand(3, 1, 512, 128)], [torch.empty(3, 1, 512, 128)])     # wrong batch: rejected, not truncated
 
 
 @pytest.mark.parametrize("precision,tol", [("bf16", 1e-2), ("tf32", 1e-3)])
