@@ -8,42 +8,60 @@
 //
 // With padded position P = p + 512:  frame t covers P in [768 t, 768 t + 1024).  Segment t =
 // [768 t, 768 t + 768) receives frame t (offset r = P - 768 t) and, for r < 256, frame t-1
-// (offset r + 768).  A 64-thread group owns 32 consecutive segments of one song and transforms 33
-// frames (the first one only for its tail), i.e. 1/32 redundant transforms and no dependency
-// between groups or CTAs.
+// (offset r + 768).  A 64-thread group owns a run of consecutive segments and transforms one extra
+// frame (the one before the run, only for its tail), so there is no dependency between groups or CTAs.
 #include "svs_common.cuh"
 #include "fft512.cuh"
 
 namespace svs {
 
 constexpr int kIstftThreads = 256;
-constexpr int kIstftRun = 32;                    // consecutive hop segments owned by one 64-thread group
 constexpr int kIstftFrFloats = 1024 + 128;                      // windowed frame, 4 floats of padding per 32 (z_addr)
 constexpr int kIstftGroupFloats = 2 * kFftScratchFloats + 2 * kIstftFrFloats;   // exchange buffer X + two windowed frames
                                                                 // (ping-pong); the current one doubles as exchange buffer Y
 constexpr size_t kIstftSmemBytes = sizeof(float) * 4 * kIstftGroupFloats + sizeof(float2) * kFftTwiddleFloat2;
 
-// One 64-thread group walks kIstftRun + 1 consecutive frames of one song: frame t-1's last 256 windowed
-// samples (its "tail") stay in shared memory and are added to the first 256 samples of frame t when the
-// group emits hop segment t.  The first frame of a run is transformed only for its tail (1/32 redundant
-// transforms), so groups and CTAs never depend on each other and every output sample is written once.
+// The batch's frames are numbered globally (songs back to back, as frame_off lays them out) and split EVENLY over
+// the 64-thread groups of a one-wave grid (3 CTAs per SM x 4 groups): group g walks the run [g R, (g+1) R) of
+// consecutive frames, crossing song borders where they fall.  Frame t-1's last 256 windowed samples (its "tail") stay
+// in shared memory and are added to the first 256 samples of frame t when hop segment t is emitted; the frame before
+// a run is transformed only for its tail (one redundant transform per run, 0.6 % for the 150-song corpus), so groups
+// never depend on each other and every output sample is written once.  (Round 1-2a: one CTA per 128 segments of one
+// song, runs of 32 -> 3 % redundant transforms and 2,250 equal CTAs over 444 resident slots, i.e. SMs with 15 or 16 of
+// them and a ragged last round.)
+constexpr int kIstftMinRun = 8;
+
 __global__ void __launch_bounds__(kIstftThreads, 3)
 istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase,
-                 const int64_t* __restrict__ frame_off, const int64_t* __restrict__ wave_off,
+                 const int64_t* __restrict__ frame_off, const int64_t* __restrict__ wave_off, int n_songs,
                  float* __restrict__ wave, float* __restrict__ song_peak,
                  const float2* __restrict__ tw1024, const float* __restrict__ hann,
                  const float* __restrict__ env_both, const float* __restrict__ env_single) {
   extern __shared__ float smem[];
-  const int song = blockIdx.y;
-  const int64_t f0 = frame_off[song];
-  const int n_frames = static_cast<int>(frame_off[song + 1] - f0);
   const int group = threadIdx.x >> 6;
   const int j = threadIdx.x & 63;
-  const int seg_begin = (blockIdx.x * 4 + group) * kIstftRun;   // first segment (= frame index) of this group
   float2* tw_table = reinterpret_cast<float2*>(smem + 4 * kIstftGroupFloats);
   const FftTwiddles tw = build_fft_twiddles(tw_table, tw1024, threadIdx.x, kIstftThreads, j);
   __syncthreads();
-  if (seg_begin >= n_frames) return;                            // whole group leaves (barriers are per group)
+  const int64_t first = frame_off[0], total = frame_off[n_songs];   // frames [first, total) of the mag / phase arrays
+  const int64_t n_groups = static_cast<int64_t>(gridDim.x) * 4;
+  int64_t run = (total - first + n_groups - 1) / n_groups;
+  if (run < kIstftMinRun) run = kIstftMinRun;
+  const int64_t g_begin = first + (static_cast<int64_t>(blockIdx.x) * 4 + group) * run;
+  if (g_begin >= total) return;                                 // whole group leaves (barriers are per group)
+  int remaining = static_cast<int>((g_begin + run <= total ? g_begin + run : total) - g_begin);   // segments to emit
+  // song of the first frame: last s with frame_off[s] <= g_begin (songs without frames are skipped by the search)
+  int song;
+  {
+    int lo = 0, hi = n_songs;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (frame_off[mid] <= g_begin) lo = mid; else hi = mid;
+    }
+    song = lo;
+  }
+  int64_t f0 = frame_off[song];
+  int n_frames = static_cast<int>(frame_off[song + 1] - f0);
   float* scratch = smem + group * kIstftGroupFloats;
   float* xre = scratch;
   float* xim = scratch + kFftScratchFloats;
@@ -76,26 +94,35 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
   // 1 / (w^2[r + 768] + w^2[r]) for the four samples r = 4 j .. 4 j + 3 < 256 this thread emits in the overlap region
   const float4 envb = __ldg(reinterpret_cast<const float4*>(env_both) + j);
 
-  const int64_t w0 = wave_off[song];
-  const int out_len = SVS_HOP * (n_frames - 1);                 // librosa: hop * (T - 1) after trimming
+  int64_t w0 = wave_off[song];
+  int out_len = SVS_HOP * (n_frames - 1);                       // librosa: hop * (T - 1) after trimming
   float peak = 0.0f;
-
-  for (int slot = 0; slot <= kIstftRun; ++slot) {
-    const int t = seg_begin - 1 + slot;
-    if (t >= n_frames) break;
-    float* const fr = fr_buf + (slot & 1) * kIstftFrFloats;
-    const float* const prev = fr_buf + ((slot & 1) ^ 1) * kIstftFrFloats;   // frame t-1: its samples 768..1023 are the tail
-    if (t < 0) {                                                // no frame before the first: empty tail
-      for (int i = j; i < 256; i += 64) fr[z_addr(SVS_HOP + i)] = 0.0f;
-      group_bar(bar);
-      continue;
+  auto flush_peak = [&]() {
+    if (song_peak != nullptr) {
+      const float m = warp_max(peak);
+      if ((threadIdx.x & 31) == 0) atomic_max_nonneg(&song_peak[song], m);
     }
+    peak = 0.0f;
+  };
+
+  // first iteration: the frame before the run, for its tail only -- or, at the start of a song, an empty tail
+  int t = static_cast<int>(g_begin - f0);
+  bool emit = t == 0;
+  int par = 0;
+  if (t == 0) {
+    for (int i = j; i < 256; i += 64) fr_buf[kIstftFrFloats + z_addr(SVS_HOP + i)] = 0.0f;   // `prev` of parity 0
+  } else {
+    --t;
+  }
+  for (;;) {
+    float* const fr = fr_buf + par * kIstftFrFloats;
+    const float* const prev = fr_buf + (par ^ 1) * kIstftFrFloats;   // frame t-1: its samples 768..1023 are the tail
     const float* __restrict__ mrow = mag + (f0 + t) * SVS_N_BINS;
     const float2* __restrict__ prow = phase + (f0 + t) * SVS_N_BINS;
-    if (t + 1 < n_frames && slot < kIstftRun) {               // pull the next frame's 6,156 bytes (49 lines) into L2
+    if (f0 + t + 1 < total && j < 17 + 33) {                   // pull the next frame's 6,156 bytes (49 lines) into L2
       const char* nxt = j < 17 ? reinterpret_cast<const char*>(mrow + SVS_N_BINS) + 128 * j
                                : reinterpret_cast<const char*>(prow + SVS_N_BINS) + 128 * (j - 17);
-      if (j < 17 + 33) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
     }
     // Z[k] = E[k] + i O[k],  E = (X[k] + conj X[512-k])/2,  O = (X[k] - conj X[512-k])/2 * conj(W^k);
     // the inverse transform is conj(FFT(conj Z)), so conj(Z) is what goes into the exchange buffer.
@@ -144,7 +171,7 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
     // A thread emits FOUR consecutive samples per step (r = 4 j + 256 c): 16-byte shared-memory loads (four samples
     // never straddle the 4-float padding every 32) and 16-byte global stores, 3 + 1 loads and 3 stores per frame
     // instead of 12 + 4 and 12.  Segment borders (p = 0, out_len) are multiples of 4, so a quad is all in or all out.
-    if (slot >= 1) {                                          // slot 0 is transformed only for its tail
+    if (emit) {
 #pragma unroll
       for (int c = 0; c < SVS_HOP / 256; ++c) {
         const int r = 4 * j + 256 * c;
@@ -162,12 +189,26 @@ istft_ola_kernel(const float* __restrict__ mag, const float2* __restrict__ phase
           peak = fmaxf(peak, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
       }
+      if (--remaining == 0) break;
+    }
+    emit = true;
+    par ^= 1;
+    if (++t >= n_frames) {                                   // the run continues in the next song
+      flush_peak();
+      do {
+        ++song;
+        f0 = frame_off[song];
+        n_frames = static_cast<int>(frame_off[song + 1] - f0);
+      } while (n_frames <= 0);                               // remaining > 0 guarantees a frame further on
+      w0 = wave_off[song];
+      out_len = SVS_HOP * (n_frames - 1);
+      t = 0;
+      // empty tail for the new song's first segment: `prev` of the next iteration is the buffer just emitted from;
+      // its tail region is read by nobody any more, and the next frame's barriers order these stores before its emit
+      for (int i = j; i < 256; i += 64) fr_buf[(par ^ 1) * kIstftFrFloats + z_addr(SVS_HOP + i)] = 0.0f;
     }
   }
-  if (song_peak != nullptr) {
-    peak = warp_max(peak);
-    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(&song_peak[song], peak);
-  }
+  flush_peak();
 }
 
 // grid (blocks per song, n_songs): no per-element song lookup, 16-byte accesses (song offsets are multiples of the
@@ -246,9 +287,14 @@ extern "C" int svs_istft_ola(const float* mag, const float* phase, const int64_t
   SVS_CUDA_TRY(cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(kIstftSmemBytes)));
   if (song_peak) SVS_CUDA_TRY(cudaMemsetAsync(song_peak, 0, sizeof(float) * n_songs, st));
-  dim3 grid(static_cast<unsigned>((max_frames + 4 * kIstftRun - 1) / (4 * kIstftRun)), n_songs);
-  istft_ola_kernel<<<grid, kIstftThreads, kIstftSmemBytes, st>>>(
-      mag, reinterpret_cast<const float2*>(phase), frame_off, wave_off, wave, song_peak, tabs.tw1024,
+  // one wave: 3 CTAs per SM (or fewer when the batch is small: a group emits at least kIstftMinRun segments)
+  const int64_t frames_bound = max_frames * n_songs;
+  int64_t ctas = static_cast<int64_t>(num_sms()) * 3;
+  const int64_t need = (frames_bound + 4 * kIstftMinRun - 1) / (4 * kIstftMinRun);
+  if (ctas > need) ctas = need;
+  if (ctas < 1) ctas = 1;
+  istft_ola_kernel<<<static_cast<unsigned>(ctas), kIstftThreads, kIstftSmemBytes, st>>>(
+      mag, reinterpret_cast<const float2*>(phase), frame_off, wave_off, n_songs, wave, song_peak, tabs.tw1024,
       tabs.hann, tabs.env_both, tabs.env_single);
   SVS_CHECK_LAUNCH("istft_ola_kernel");
   return SVS_OK;
