@@ -50,9 +50,11 @@ struct ZcParams {
   long long* dbg;                // profiling: per CTA 64 clock64 stamps
 };
 
-template <int kBlockN, int kASlots, int kBSlots, int kRow>
+// kStoreBytes: staging ring of the TMA-store epilogue (0 = per-thread global stores)
+template <int kBlockN, int kASlots, int kBSlots, int kRow, int kStoreBytes = 0>
 constexpr size_t zc_smem_bytes() {
-  return static_cast<size_t>(kASlots) * zc_a_slot<kRow>() + static_cast<size_t>(kBSlots) * kBlockN * kRow + 1024 + 1024 + 2048;
+  return static_cast<size_t>(kASlots) * zc_a_slot<kRow>() + static_cast<size_t>(kBSlots) * kBlockN * kRow + kStoreBytes +
+         1024 + 1024 + 2048;
 }
 
 __device__ __forceinline__ float zc_act(float v, int act) {
@@ -82,20 +84,20 @@ __device__ __forceinline__ void zc_store16(float* dst, const float (&f)[16]) {  
 // tap set known at compile time the issue loop unrolls into straight-line code whose descriptors are
 // "slab base + constant".  kmask(s, dy, dx) = active 32-byte k-steps of tap (dy, dx) of slab s, 0 = no tap;
 // the order (s, dy, dx ascending, inactive skipped) is the order zc_plan_layer() packs the weights in.
-struct ZcRuntimeTaps { static constexpr bool kStatic = false; static constexpr int kSlabs = 0;
+struct ZcRuntimeTaps { static constexpr bool kStatic = false; static constexpr int kSlabs = 0; static constexpr bool kMerged = false;
   __host__ __device__ static constexpr int kmask(int, int, int) { return 0; } };
 template <int kNSlabs> struct ZcDeconvTaps {      // phase-merged deconv: every slab uses all 9 shifts, full K
-  static constexpr bool kStatic = true; static constexpr int kSlabs = kNSlabs;
+  static constexpr bool kStatic = true; static constexpr int kSlabs = kNSlabs; static constexpr bool kMerged = true;
   __host__ __device__ static constexpr int kmask(int, int, int) { return 0xF; } };
 struct ZcConv2Taps {                              // Ct = 32: row = [pw0: d-half | skip | pw1: d-half | skip]; slab = ph
-  static constexpr bool kStatic = true; static constexpr int kSlabs = 2;
+  static constexpr bool kStatic = true; static constexpr int kSlabs = 2; static constexpr bool kMerged = false;
   __host__ __device__ static constexpr int kmask(int s, int dy, int dx) { return (2 * dy + s + 2 > 4) ? 0 : (dx <= 0 ? 0xA : 0x2); } };
 struct ZcConvParity2Taps {                        // two 128-byte channel windows per column parity (TF32 conv4):
-  static constexpr bool kStatic = true; static constexpr int kSlabs = 8;   // slab = ph*4 + pw*2 + window
+  static constexpr bool kStatic = true; static constexpr int kSlabs = 8; static constexpr bool kMerged = false;   // slab = ph*4 + pw*2 + window
   __host__ __device__ static constexpr int kmask(int s, int dy, int dx) {
     return (2 * dy + (s >> 2) + 2 > 4 || 2 * dx + ((s >> 1) & 1) + 2 > 4) ? 0 : 0xF; } };
 template <int kKMask> struct ZcConvParityTaps {   // slabs (ph, pw) = (s >> 1, s & 1): conv3 (skip half = 0xC), conv4 (0xF)
-  static constexpr bool kStatic = true; static constexpr int kSlabs = 4;
+  static constexpr bool kStatic = true; static constexpr int kSlabs = 4; static constexpr bool kMerged = false;
   __host__ __device__ static constexpr int kmask(int s, int dy, int dx) {
     return (2 * dy + (s >> 1) + 2 > 4 || 2 * dx + (s & 1) + 2 > 4) ? 0 : kKMask; } };
 
@@ -135,11 +137,22 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
 // kDual: the CTA works on TWO neighbouring M tiles at once (two accumulators per TMEM stage, a slab slot holds both
 // tiles' halo slabs) and every streamed weight chunk feeds both: the layer is bound by bytes streamed into the SM, and
 // this halves the weight bytes per MMA without a cluster.  N <= 128 (4 x N TMEM columns).
+// kStoreUnits > 0: TMA-STORE EPILOGUE.  The per-thread stores of the plain epilogue are 16-byte pieces at one pixel
+// pitch per lane: 32 cache lines = 32 LSU wavefronts per instruction, 2,048 per 128 x 128 tile, which is what the
+// 3.6k-cycle exposed epilogue of the one-tile-per-CTA layers was.  Here a thread writes its 32 accumulator columns
+// into a shared-memory unit laid out as the TMA box(es) of the step (rows of 32 / 64 / 128 bytes in the matching
+// TMA swizzle: row-per-lane 16-byte stores are conflict free in all three), and one elected thread hands the unit to
+// the TMA engine (cp.async.bulk.tensor.5d.global.shared: UTMASTG).  Units form a ring of kStoreUnits; the issuing
+// thread waits for the store kStoreUnits - 1 steps back to have READ its unit before the barrier that lets the
+// others fill the next one, so there is one 128-thread barrier per 32 columns.  The output is addressed through a
+// 5-D map (channel, px, x, py, batch * grid rows + y): conv layers have px = py = 1, merged deconvs store one
+// sub-pixel phase per box.  kStoreAlias (launches with ONE tile per CTA, i.e. batch 64): the ring lives in the slab
+// slots, which are dead once the tile's MMAs have retired, so the operand rings keep their full depth.
 template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1,
-          bool kTrim = false, bool kDual = false>
+          bool kTrim = false, bool kDual = false, int kStoreUnits = 0, bool kStoreAlias = false>
 __global__ void __launch_bounds__(kZcThreads)
 zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ ZcParams p) {
+               const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ ZcParams p) {
   static_assert(kCluster == 1 || kCluster == 2, "CTA pairs only");
   static_assert(!kTrim || (kCluster == 1 && kRow == 128 && Taps::kStatic && kBlockN % 64 == 0), "trimmed form");
   static_assert(!kDual || (kCluster == 1 && !kTrim && Taps::kStatic && kBlockN <= 128), "dual-tile form");
@@ -153,12 +166,17 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int kStageCols = kTiles * kAccCols;                   // accumulator columns of one TMEM stage
   constexpr int kTmemCols = 2 * kStageCols;
   constexpr int kNBar = 2 * kBSlots + 2 * kASlots + 4;
+  constexpr int kUnitBytes = 128 * 32 * static_cast<int>(sizeof(OutT));     // one 32-column step of the tile
+  constexpr int kStoreBytes = kStoreAlias ? 0 : kStoreUnits * kUnitBytes;
+  static_assert(kStoreUnits == 0 || (kStoreUnits >= 2 && !kDual && kBlockN % 32 == 0), "store ring");
+  static_assert(!kStoreAlias || kStoreUnits * kUnitBytes <= kASlots * kZcASlot, "aliased store ring fits the slab slots");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t b_base = smem_base + kASlots * kZcASlot;
-  const size_t bar_off = static_cast<size_t>(kASlots) * kZcASlot + static_cast<size_t>(kBSlots) * kBBytes;
+  const uint32_t store_base = kStoreAlias ? smem_base : b_base + kBSlots * kBBytes;   // 1024-byte aligned: slots and chunks are
+  const size_t bar_off = static_cast<size_t>(kASlots) * kZcASlot + static_cast<size_t>(kBSlots) * kBBytes + kStoreBytes;
   const uint32_t bar_base = smem_base + static_cast<uint32_t>(bar_off);
   auto full_b = [&](int s) { return bar_base + 8u * s; };
   auto empty_b = [&](int s) { return bar_base + 8u * (kBSlots + s); };
@@ -185,6 +203,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     fence_barrier_init();
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (kStoreUnits > 0) tma_prefetch_desc(&tmap_o);
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   pdl_launch_dependents();
@@ -405,15 +424,118 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
   } else {
     // ===== epilogue =====
-    pdl_wait();                                   // before the first global store
+    if constexpr (kStoreUnits == 0) pdl_wait();   // before the first global store
     const int q = warp & 3;
     const int r = 32 * q + lane;
     const int ix = r & 7, iy = r >> 3;
     int t = 0;
+    int store_step = 0;                           // TMA-store epilogue: 32-column steps since the kernel started
     OutT* const out_base = reinterpret_cast<OutT*>(p.out);
     const float slope = p.act == ACT_LEAKY ? 0.2f : 0.0f;
     const int cp_log2 = 31 - __clz(p.cout_phase), cp_mask = p.cout_phase - 1;   // channels per phase: a power of two
     const uint32_t out_pitch = p.out_pitch, out_coff = p.out_coff;
+    if constexpr (kStoreUnits > 0) {
+      // ---- TMA-store epilogue (see the kernel comment) ----
+      constexpr int kEs = static_cast<int>(sizeof(OutT));
+      constexpr int kPhaseCols = Taps::kMerged ? kBlockN / 4 : kBlockN;      // contiguous channels of one pixel
+      constexpr int kBoxCols = kPhaseCols < 32 ? kPhaseCols : 32;            // channels per TMA box
+      constexpr int kBoxW = kBoxCols * kEs;                                  // bytes per box row: 32 / 64 / 128
+      constexpr int kBoxes = 32 / kBoxCols;                                  // boxes per 32-column step
+      static_assert(kBoxW == 32 || kBoxW == 64 || kBoxW == 128, "box row = one TMA swizzle span");
+      static_assert(kStoreUnits <= 4, "one issuing warp per unit");
+      constexpr int kChunks = kBoxW / 16;
+      // XOR of the 16-byte chunk index inside a box row: TMA's swizzle is a function of the shared-memory address
+      const uint32_t swz = kBoxW == 128 ? (r & 7) : kBoxW == 64 ? ((r >> 1) & 3) : ((r >> 2) & 1);
+      // unit u is stored (and its bulk groups are waited for) by lane 0 of epilogue warp u: the ~150 cycles of
+      // coordinate set-up + issue rotate over the four warps instead of holding up one of them at every barrier
+      const int my_unit = lane == 0 ? q : -1;
+      // Pass -1 is a DRY RUN (no tile, nothing stored, nothing signalled) made while the MMAs of the first tile are
+      // still running: the epilogue is ~2 KB of straight-line code that would otherwise be fetched cold at the one
+      // moment it is on the critical path (measured: 560 cycles before the first column and 720 instead of 350 for
+      // the first 32-column step).  One loop body serves both passes so that the compiler cannot specialise it.
+#pragma unroll 1
+      for (int it = -1, unit = blockIdx.x; it < 0 || unit < total_tiles; ++it) {
+        const bool live = it >= 0;
+        const int as = it & 1;
+        if (live) {
+          if (it == 0) pdl_wait();                         // before the first global store
+          mbar_wait(tmem_full(as), (it >> 1) & 1);
+          if (dbg && it < 8 && threadIdx.x == 64) dbg[32 + it] = clock64();
+          tc_fence_after();
+        }
+        const int tw = unit % p.ntw, th = (unit / p.ntw) % p.nth, b = unit / (p.ntw * p.nth);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + as * kStageCols;
+#pragma unroll 1
+        for (int c = 0; c < kBlockN; c += 32) {
+          uint32_t v[32];
+          tmem_ld16(taddr + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld16(taddr + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          tmem_ld_wait();
+          const int cur = store_step % kStoreUnits;
+          const uint32_t ubase = store_base + cur * kUnitBytes;
+#pragma unroll
+          for (int bx = 0; bx < kBoxes; ++bx) {
+            const uint32_t row = ubase + bx * (128 * kBoxW) + r * kBoxW;
+            const int ch0 = (c + bx * kBoxCols) & (kPhaseCols - 1);           // channel of the box's first column
+#pragma unroll
+            for (int k = 0; k < kChunks; ++k) {
+              constexpr int kPer = 16 / kEs;                                   // values per 16-byte chunk
+              float f[kPer];
+#pragma unroll
+              for (int i = 0; i < kPer; i += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(&sbias[ch0 + k * kPer + i]);
+                const int vi = bx * kBoxCols + k * kPer + i;
+                const float t0 = __uint_as_float(v[vi]) + bv.x, t1 = __uint_as_float(v[vi + 1]) + bv.y;
+                const float t2 = __uint_as_float(v[vi + 2]) + bv.z, t3 = __uint_as_float(v[vi + 3]) + bv.w;
+                f[i] = fmaxf(t0, fmaf(slope, t0, 0.0f));
+                f[i + 1] = fmaxf(t1, fmaf(slope, t1, 0.0f));
+                f[i + 2] = fmaxf(t2, fmaf(slope, t2, 0.0f));
+                f[i + 3] = fmaxf(t3, fmaf(slope, t3, 0.0f));
+              }
+              uint32_t w[4];
+              if constexpr (kEs == 2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                  w[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[i] = __float_as_uint(round_tf32(f[i]));
+              }
+              if (!kStoreAlias || live)                    // aliased ring: the dry run must not touch the slab slots
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((static_cast<uint32_t>(k) ^ swz) << 4)),
+                             "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                             : "memory");
+            }
+          }
+          if (live && c + 32 >= kBlockN) {                 // last TMEM read of the tile: the MMAs may refill the stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(as));
+          }
+          fence_proxy_async();                             // the unit is read by the async proxy
+          if (my_unit == (cur + 1) % kStoreUnits) bulk_wait_group_read<0>();   // the NEXT step's unit has been read out
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (live && my_unit == cur) {
+#pragma unroll
+            for (int bx = 0; bx < kBoxes; ++bx) {
+              const int col = c + bx * kBoxCols;
+              const int ph = Taps::kMerged ? col / kPhaseCols : 0;
+              tma_store_5d(&tmap_o, ubase + bx * (128 * kBoxW), static_cast<int>(out_coff) + (col & (kPhaseCols - 1)), ph & 1,
+                           tw * kZcBw, ph >> 1, b * p.nth * kZcBh + th * kZcBh);
+            }
+            bulk_commit_group();
+          }
+          if (live) ++store_step;
+        }
+        if (live) {
+          if (dbg && it < 8 && threadIdx.x == 64) dbg[40 + it] = clock64();
+          unit += gridDim.x;
+        }
+      }
+      if (my_unit >= 0) bulk_wait_group_all();             // every store of this CTA has been written before it exits
+    } else
     for (int unit = blockIdx.x; unit < total_tiles; unit += gridDim.x, ++t) {
       const int as = t & 1;
       mbar_wait(tmem_full(as), (t >> 1) & 1);
@@ -638,12 +760,16 @@ void zc_free_layers(svs_unet_plan* plan) {
 }
 
 template <typename OutT, bool kTf32, int kBlockN, int kASlots, int kBSlots, typename Taps, int kRow = 128, int kCluster = 1,
-          bool kTrim = false, bool kDual = false>
-static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcParams& p, cudaStream_t st) {
-  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps, kRow, kCluster, kTrim, kDual>;
+          bool kTrim = false, bool kDual = false, int kStoreUnits = 0, bool kStoreAlias = false>
+static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcParams& p, cudaStream_t st,
+                       const CUtensorMap* to = nullptr) {
+  auto kern = zc_conv_kernel<OutT, kTf32, kBlockN, kASlots, kBSlots, Taps, kRow, kCluster, kTrim, kDual, kStoreUnits, kStoreAlias>;
   constexpr int kTiles = kDual ? 2 : 1;
-  constexpr size_t smem = zc_smem_bytes<kBlockN, kTiles * kASlots, kBSlots, kRow>();
+  constexpr size_t smem = zc_smem_bytes<kBlockN, kTiles * kASlots, kBSlots, kRow,
+                                        kStoreAlias ? 0 : kStoreUnits * 128 * 32 * static_cast<int>(sizeof(OutT))>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
+  if (kStoreUnits > 0 && to == nullptr) return fail(SVS_ERR_INVALID_ARG, "zc_launch_t: output tensor map missing");
+  const CUtensorMap& tmo = to ? *to : ta;            // unused by the plain epilogue
   SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   constexpr int kAccCols = kBlockN < 32 ? 32 : kBlockN;
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
@@ -653,7 +779,7 @@ static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcPar
   int grid = num_sms() * per_sm;
   if (grid > p.m_tiles / kTiles) grid = p.m_tiles / kTiles;
   if constexpr (kCluster == 1) {
-    SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, ta, tb, p));
+    SVS_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, ta, tb, tmo, p));
   } else {
     grid &= ~1;                                      // whole CTA pairs; the caller guarantees an even tile count
     cudaLaunchConfig_t cfg{};
@@ -665,7 +791,7 @@ static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcPar
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    SVS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    SVS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tmo, p));
   }
   return SVS_OK;
 }
@@ -710,6 +836,44 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   p.resident = z.resident ? 1 : 0;
   p.dbg = (g_tc_dbg_layer == li) ? g_tc_dbg : nullptr;
   const int n = z.n_total;
+  // TMA-store epilogue (bf16 layers whose shared-memory budget has room for the staging ring): on by default,
+  // SVS_ZC_TMASTORE=0 keeps the per-thread stores
+  static const bool tma_store = [] { const char* e = std::getenv("SVS_ZC_TMASTORE"); return !(e && e[0] == '0'); }();
+  static const bool experiments = [] {            // the opt-in variants below keep the plain epilogue
+    for (const char* name : {"SVS_ZC_MCAST", "SVS_ZC_TRIM", "SVS_ZC_RING", "SVS_ZC_DUAL"}) {
+      const char* e = std::getenv(name);
+      if (e && e[0] != '0') return true;
+    }
+    return false;
+  }();
+  if (tma_store && !tf32 && !experiments && (li == 2 || li == 3 || li == 8 || li == 10)) {
+    // 5-D output view (channel, px, x, py, batch * grid rows + y); conv layers: px = py = 1
+    CUtensorMap to;
+    const cuuint64_t pitch = kBufGeom[g.out_buf].c, sc = g.transposed ? 2 : 1;
+    const cuuint64_t dims[5] = {pitch, sc, static_cast<cuuint64_t>(gw), sc, static_cast<cuuint64_t>(gh) * batch};
+    const cuuint64_t strides[4] = {pitch * es, sc * pitch * es, static_cast<cuuint64_t>(g.wout) * pitch * es,
+                                   sc * g.wout * pitch * es};
+    const int box_cols = g.cout < 32 ? g.cout : 32;
+    const cuuint32_t box[5] = {static_cast<cuuint32_t>(box_cols), 1, kZcBw, 1, kZcBh};
+    int rc = encode_tensor_map(&to, tf32, 5, ws.buf[g.out_buf], dims, strides, box, box_cols * es, 0);
+    if (rc != SVS_OK) return rc;
+#define SVS_ZC_STORE(LI, N, AS, BS, RES, TAPS, ROW, UNITS)                                              \
+    if (li == LI && n == N && z.resident == RES && z.row_bytes == ROW && z.sch.n_slabs == TAPS::kSlabs && \
+        (!RES || z.sch.n_taps == BS))                                                                     \
+      return zc_launch_t<__nv_bfloat16, false, N, AS, BS, TAPS, ROW, 1, false, false, UNITS>(ta, z.tmap_b, p, st, &to);
+    // one tile per CTA (batch <= 74): full-depth operand rings, the store ring aliases the slab slots; larger
+    // batches keep the plain epilogue for these two layers (a dedicated ring would cost a ring slot each, measured
+    // slower: conv4 13.5 vs 12.8 us, deconv3 21.0 vs 19.8 us at batch 64)
+    if (p.m_tiles <= num_sms()) {
+      if (li == 3 && n == 128 && !z.resident && z.sch.n_slabs == 4)
+        return zc_launch_t<__nv_bfloat16, false, 128, 5, 6, ZcConvParityTaps<0xF>, 128, 1, false, false, 4, true>(ta, z.tmap_b, p, st, &to);
+      if (li == 8 && n == 256 && !z.resident && z.sch.n_slabs == 4)
+        return zc_launch_t<__nv_bfloat16, false, 256, 3, 4, ZcDeconvTaps<4>, 128, 1, false, false, 4, true>(ta, z.tmap_b, p, st, &to);
+    }
+    SVS_ZC_STORE(2, 64, 6, 25, true, ZcConvParityTaps<0x3>, 64, 2)       // conv3 (narrow rows, resident weights)
+    SVS_ZC_STORE(10, 64, 4, 9, true, ZcDeconvTaps<1>, 128, 4)            // deconv5: 96 + 72 + 32 KB
+#undef SVS_ZC_STORE
+  }
   // bf16 layers of the reference network get compile-time tap tables; anything else (TF32 rows are 32
   // channels wide, so the slab/tap sets differ) runs the same kernel with the runtime schedule
 #define SVS_ZC_NARROW(TF, LI, N, AS, BS, TAPS, ROW)                                                     \

@@ -39,6 +39,9 @@ def main():
         print("   MMA done issuing tile0-7", [med(24 + j) for j in range(8)])
         print("   epilogue start tile0-7 ", [med(32 + j) for j in range(8)])
         print("   epilogue end   tile0-7 ", [med(40 + j) for j in range(8)])
+        if (t[:, 48] > 0).any():                       # TMA-store epilogue: stamps inside the first two 32-column steps
+            print("   store step 0 [ld issue, ld done, smem written, store ring free, barrier, TMA issued]", [med(48 + j) for j in range(6)])
+            print("   store step 1", [med(54 + j) for j in range(6)])
 
 
 if __name__ == "__main__":
