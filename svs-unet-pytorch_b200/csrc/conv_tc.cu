@@ -604,8 +604,8 @@ int tc_cluster_mode() {
   static const int mode = [] { const char* e = std::getenv("SVS_TC_CLUSTER"); return e ? std::atoi(e) : 2; }();
   return mode;
 }
-bool ck_supported(const TcLayer& t, int split);
-int ck_launch_layer(const TcLayer& t, bool tf32, const CUtensorMap& ta, const TcParams& p, cudaStream_t st);
+bool ck_supported(const TcLayer& t, int split, int block_n);
+int ck_launch_layer(const TcLayer& t, bool tf32, int block_n, const CUtensorMap& ta, const TcParams& p, cudaStream_t st);
 
 // Tiling of one problem at one batch size: M tiles, the N tile (a layer with has_wide may use 256) and split-K.
 void tc_tiling(const TcLayer& t, int batch, int* m_tiles, int* split_k, int* block_n) {
@@ -637,6 +637,23 @@ void tc_tiling(const TcLayer& t, int batch, int* m_tiles, int* split_k, int* blo
     const int cost_narrow = (tiles + sms - 1) / sms * 32, cost_wide = (wide_tiles + sms - 1) / sms * 48;
     if (cost_wide < cost_narrow) *block_n = 256;
   }
+  // Cluster split-K on 128 x 256 tiles: half the tiles, twice the split, a quarter less operand traffic per MAC.
+  // OFF by default (SVS_CK_WIDE=1): parity-tested, measured at batch 64 bf16 conv5 12.7 vs 12.9 us, deconv1 15.0 vs
+  // 15.5 us, conv6 24.9 vs 13.3 us (sixteen clusters of EIGHT 200 KB CTAs do not all find a GPC in one wave).  The
+  // halved A-chunk count and the quarter less traffic do not shorten the main loop, i.e. these layers are not bound by
+  // bytes into shared memory either; the doubled split makes the DSMEM reduction longer.
+  static const bool ck_wide = [] { const char* w = std::getenv("SVS_CK_WIDE"); return w && w[0] == '1'; }();
+  if (t.has_wide && s > 1 && tc_cluster_mode() == 2 && !e && !no_wide && ck_wide) {
+    const int wide_tiles = *m_tiles * (n_total / 256) * t.n_phases;
+    int sw = 148 / wide_tiles;
+    if (sw > 8) sw = 8;
+    if (sw > min_chunks / 4) sw = min_chunks / 4;
+    while (sw & (sw - 1)) --sw;
+    if (sw >= 2 && wide_tiles * sw >= tiles * s && ck_supported(t, sw, 256)) {
+      *block_n = 256;
+      *split_k = sw;
+    }
+  }
 }
 
 size_t tc_splitk_bytes_one(const TcLayer& t, int batch) {
@@ -659,7 +676,7 @@ size_t tc_splitk_bytes(const svs_unet_plan* plan, int batch) {
 int tc_launch_count(const svs_unet_plan* plan, int li, int batch) {
   int m_tiles, split, block_n;
   tc_tiling(plan->tc[li], batch, &m_tiles, &split, &block_n);
-  if (split > 1 && tc_cluster_mode() == 2 && ck_supported(plan->tc[li], split)) return 1;
+  if (split > 1 && tc_cluster_mode() == 2 && ck_supported(plan->tc[li], split, block_n)) return 1;
   return split > 1 ? 2 : 1;   // main kernel (+ split-K reduction)
 }
 
@@ -742,8 +759,8 @@ int tc_launch(const TcLayer& t, const TcIo& io, int batch, bool tf32, cudaStream
   const int grid = m_tiles * p.n_tiles * t.n_phases * split;
   int rc = SVS_ERR_NOT_IMPLEMENTED;
   bool finish = split > 1;
-  if (tc_cluster_mode() == 2 && split > 1 && ck_supported(t, split)) {
-    rc = ck_launch_layer(t, tf32, ta, p, st);           // split-K inside a cluster: no partials, no finish kernel
+  if (tc_cluster_mode() == 2 && split > 1 && ck_supported(t, split, block_n)) {
+    rc = ck_launch_layer(t, tf32, block_n, ta, p, st);  // split-K inside a cluster: no partials, no finish kernel
     finish = false;
   } else if (split > 1 && io.splitk_bytes < static_cast<size_t>(split) * t.n_phases * p.m_pad * g.cout * sizeof(float)) {
     return fail(SVS_ERR_WORKSPACE, "tc_launch: split-K scratch too small");

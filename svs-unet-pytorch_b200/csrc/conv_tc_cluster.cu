@@ -32,9 +32,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 
-constexpr int kCkBlockN = 128;
-constexpr int kCkStages = 6;
-constexpr size_t kCkSmemBytes = static_cast<size_t>(kCkStages) * (128 + kCkBlockN) * 128 + 1024 + 256 + 2048;
+// N tile 128 (six 32 KB stages) or 256 (four 48 KB stages): the deep layers are bound by bytes INTO shared memory,
+// and a 128 x 256 tile moves 48 KB per K chunk for twice the MACs of a 128 x 128 tile's 32 KB.  With the tile count
+// halved the K split doubles, so the grid still fills the SMs (conv5: 32 tiles x 4, conv6: 16 x 8, deconv1: 32 x 4).
+
+constexpr size_t kCkSmemBytes = static_cast<size_t>(6) * (128 + 128) * 128 + 1024 + 256 + 2048;   // same for both shapes
+static_assert(static_cast<size_t>(4) * (128 + 256) * 128 == static_cast<size_t>(6) * (128 + 128) * 128, "ring bytes");
 
 
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
@@ -52,9 +55,10 @@ __device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
 __device__ __forceinline__ void st_smem_f4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// accumulator parking lot: row r = 512 bytes, 16-byte chunk c at (c ^ (r & 31)): conflict-free both for the
-// row-per-thread TMEM drain and for the chunk-per-thread reduction
-__device__ __forceinline__ uint32_t park_off(int r, int c) { return static_cast<uint32_t>(r * 512 + ((c ^ (r & 31)) << 4)); }
+// accumulator parking lot: row r = 4 * kBlockN bytes, 16-byte chunk c at (c ^ (r & 31)): conflict-free both for the
+// row-per-thread TMEM drain and for the chunk-per-thread reduction (the XOR stays inside a 32-chunk half)
+template <int kBlockN>
+__device__ __forceinline__ uint32_t park_off(int r, int c) { return static_cast<uint32_t>(r * (4 * kBlockN) + ((c ^ (r & 31)) << 4)); }
 
 __device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&o)[4]) {
   __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
@@ -75,16 +79,16 @@ __device__ __forceinline__ void store4(float* dst, const float (&o)[4], int out_
 }
 __device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&o)[4], int) { store4(dst, o); }
 
-template <typename OutT, bool kTf32, int kSplit>
+template <typename OutT, bool kTf32, int kSplit, int kBlockN>
 __global__ void __launch_bounds__(kTcThreads)
 tc_conv_ck_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b0,
                   const __grid_constant__ CUtensorMap tmap_b1, const __grid_constant__ CUtensorMap tmap_b2,
                   const __grid_constant__ CUtensorMap tmap_b3, const TcParams p) {
-  constexpr int kBlockN = kCkBlockN, kStages = kCkStages, kSwz = 128;
+  constexpr int kStages = kBlockN == 128 ? 6 : 4, kSwz = 128;
   constexpr int kABytes = 128 * kSwz, kBBytes = kBlockN * kSwz, kStageBytes = kABytes + kBBytes;
   constexpr int kTmemCols = kBlockN;
   constexpr int kRowsPerCta = 128 / kSplit;
-  static_assert(kStages * kStageBytes >= 128 * 512, "the operand ring doubles as the accumulator parking lot");
+  static_assert(kStages * kStageBytes >= 128 * 4 * kBlockN, "the operand ring doubles as the accumulator parking lot");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -190,7 +194,7 @@ tc_conv_ck_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        st_smem_f4(smem_base + park_off(r, (c >> 2) + i), __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+        st_smem_f4(smem_base + park_off<kBlockN>(r, (c >> 2) + i), __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
     }
     tc_fence_before();
@@ -205,8 +209,6 @@ tc_conv_ck_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // reduce rows [rank * kRowsPerCta, +kRowsPerCta): a warp handles one row per step, lane = 4-channel chunk
     const int e = threadIdx.x - 64;
     const int chunk = e & 31;
-    const int n = nt * kBlockN + 4 * chunk;
-    const float4 bv = *reinterpret_cast<const float4*>(&sbias[n]);
     OutT* const out_base = reinterpret_cast<OutT*>(p.out);
     const int py = p.py[phase], px = p.px[phase];
     // One warp per scheduler and nothing left to overlap with: the loop is bound by dependent-issue latency, so
@@ -217,35 +219,40 @@ tc_conv_ck_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int k = 0; k < kSplit; ++k) peer[k] = map_to_cta(smem_after, k);
     const int sh = p.bw_log2 + p.bh_log2;
     const size_t pix_pitch = static_cast<size_t>(p.out_pitch);
-    OutT* const out_n = out_base + p.out_coff + n;
     constexpr int kBatch = 16 / kSplit;              // rows in flight: 16 loads per thread
     static_assert((kRowsPerCta / 4) % kBatch == 0, "rows per CTA must be a multiple of the load batch");
 #pragma unroll 1
-    for (int i0 = 0; i0 < kRowsPerCta / 4; i0 += kBatch) {
-      float4 v[kBatch][kSplit];
+    for (int half = 0; half < kBlockN / 128; ++half) {     // a warp covers 128 channels of a row per step
+      const int n = nt * kBlockN + 128 * half + 4 * chunk;
+      const float4 bv = *reinterpret_cast<const float4*>(&sbias[n]);
+      OutT* const out_n = out_base + p.out_coff + n;
+#pragma unroll 1
+      for (int i0 = 0; i0 < kRowsPerCta / 4; i0 += kBatch) {
+        float4 v[kBatch][kSplit];
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const int r = static_cast<int>(rank) * kRowsPerCta + 4 * (i0 + j) + (e >> 5);
-        const uint32_t off = park_off(r, chunk);
+        for (int j = 0; j < kBatch; ++j) {
+          const int r = static_cast<int>(rank) * kRowsPerCta + 4 * (i0 + j) + (e >> 5);
+          const uint32_t off = park_off<kBlockN>(r, 32 * half + chunk);
 #pragma unroll
-        for (int k = 0; k < kSplit; ++k) v[j][k] = ld_cluster_f4(peer[k] + off);
-      }
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const int r = static_cast<int>(rank) * kRowsPerCta + 4 * (i0 + j) + (e >> 5);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < kSplit; ++k) {          // fixed order: deterministic
-          acc.x += v[j][k].x; acc.y += v[j][k].y; acc.z += v[j][k].z; acc.w += v[j][k].w;
+          for (int k = 0; k < kSplit; ++k) v[j][k] = ld_cluster_f4(peer[k] + off);
         }
-        const int iw = r & (p.bw - 1), ih = (r >> p.bw_log2) & (p.bh - 1), ib = r >> sh;
-        const int gx = tw * p.bw + iw, gy = th * p.bh + ih, b = tb * p.nb + ib;
-        const int oy = gy * p.out_scale + py, ox = gx * p.out_scale + px;
-        // max(v, slope * v + 0): LeakyReLU (0.2), ReLU (0) and identity (1) without a branch
-        const float t[4] = {acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w};
-        const float o[4] = {fmaxf(t[0], fmaf(slope, t[0], 0.0f)), fmaxf(t[1], fmaf(slope, t[1], 0.0f)),
-                            fmaxf(t[2], fmaf(slope, t[2], 0.0f)), fmaxf(t[3], fmaf(slope, t[3], 0.0f))};
-        if (b < p.batch) store4(out_n + static_cast<size_t>((b * p.hout + oy) * p.wout + ox) * pix_pitch, o, p.out_flags);
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+          const int r = static_cast<int>(rank) * kRowsPerCta + 4 * (i0 + j) + (e >> 5);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < kSplit; ++k) {          // fixed order: deterministic
+            acc.x += v[j][k].x; acc.y += v[j][k].y; acc.z += v[j][k].z; acc.w += v[j][k].w;
+          }
+          const int iw = r & (p.bw - 1), ih = (r >> p.bw_log2) & (p.bh - 1), ib = r >> sh;
+          const int gx = tw * p.bw + iw, gy = th * p.bh + ih, b = tb * p.nb + ib;
+          const int oy = gy * p.out_scale + py, ox = gx * p.out_scale + px;
+          // max(v, slope * v + 0): LeakyReLU (0.2), ReLU (0) and identity (1) without a branch
+          const float t[4] = {acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w};
+          const float o[4] = {fmaxf(t[0], fmaf(slope, t[0], 0.0f)), fmaxf(t[1], fmaf(slope, t[1], 0.0f)),
+                              fmaxf(t[2], fmaf(slope, t[2], 0.0f)), fmaxf(t[3], fmaf(slope, t[3], 0.0f))};
+          if (b < p.batch) store4(out_n + static_cast<size_t>((b * p.hout + oy) * p.wout + ox) * pix_pitch, o, p.out_flags);
+        }
       }
     }
   }
@@ -261,14 +268,15 @@ tc_conv_ck_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
-bool ck_supported(const TcLayer& t, int split) {
+bool ck_supported(const TcLayer& t, int split, int block_n) {
   const bool pow2 = !(t.bw & (t.bw - 1)) && !(t.bh & (t.bh - 1));     // pixel decode by shifts in the reduction
-  return t.enabled && !t.merged && pow2 && t.swz == 128 && t.block_n == 128 && (split == 2 || split == 4 || split == 8);
+  const bool shape = block_n == 128 ? t.block_n == 128 : (block_n == 256 && t.has_wide);
+  return t.enabled && !t.merged && pow2 && t.swz == 128 && shape && (split == 2 || split == 4 || split == 8);
 }
 
-template <typename OutT, bool kTf32, int kSplit>
+template <typename OutT, bool kTf32, int kSplit, int kBlockN>
 static int launch_ck(const CUtensorMap& ta, const TcLayer& t, const TcParams& p, cudaStream_t st) {
-  auto kern = tc_conv_ck_kernel<OutT, kTf32, kSplit>;
+  auto kern = tc_conv_ck_kernel<OutT, kTf32, kSplit, kBlockN>;
   SVS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCkSmemBytes)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.m_tiles * p.n_tiles * p.n_phases * kSplit);
@@ -282,19 +290,23 @@ static int launch_ck(const CUtensorMap& ta, const TcLayer& t, const TcParams& p,
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  SVS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, t.tmap_b[0], t.tmap_b[1], t.tmap_b[2], t.tmap_b[3], p));
+  const CUtensorMap* tb = kBlockN == 256 ? t.tmap_b_wide : t.tmap_b;
+  SVS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb[0], tb[1], tb[2], tb[3], p));
   return SVS_OK;
 }
 
-int ck_launch_layer(const TcLayer& t, bool tf32, const CUtensorMap& ta, const TcParams& p, cudaStream_t st) {
-#define SVS_CK_CASE(S)                                                                     \
-  if (p.split_k == S)                                                                      \
-    return tf32 ? launch_ck<float, true, S>(ta, t, p, st) : launch_ck<__nv_bfloat16, false, S>(ta, t, p, st);
-  SVS_CK_CASE(2)
-  SVS_CK_CASE(4)
-  SVS_CK_CASE(8)
+int ck_launch_layer(const TcLayer& t, bool tf32, int block_n, const CUtensorMap& ta, const TcParams& p, cudaStream_t st) {
+#define SVS_CK_CASE(S, N)                                                                  \
+  if (p.split_k == S && block_n == N)                                                      \
+    return tf32 ? launch_ck<float, true, S, N>(ta, t, p, st) : launch_ck<__nv_bfloat16, false, S, N>(ta, t, p, st);
+  SVS_CK_CASE(2, 128)
+  SVS_CK_CASE(4, 128)
+  SVS_CK_CASE(8, 128)
+  SVS_CK_CASE(2, 256)
+  SVS_CK_CASE(4, 256)
+  SVS_CK_CASE(8, 256)
 #undef SVS_CK_CASE
-  return fail(SVS_ERR_NOT_IMPLEMENTED, "ck_launch_layer: unsupported split");
+  return fail(SVS_ERR_NOT_IMPLEMENTED, "ck_launch_layer: unsupported split / tile");
 }
 
 }  // namespace svs

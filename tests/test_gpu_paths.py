@@ -48,6 +48,7 @@ VARIANTS = {
     "full_width_slab_rows": {"SVS_ZC_NARROW": "0"},
     "phase_trimmed_merged_deconv": {"SVS_ZC_TRIM": "1"},                # deconv3 / deconv4 taps only over the phase blocks they reach
     "dual_tiles_per_weight_pass": {"SVS_ZC_DUAL": "1", "SVS_TEST_BATCH": "160"},   # conv4 / deconv4: two M tiles per CTA step
+    "wide_cluster_tiles": {"SVS_CK_WIDE": "1"},                         # conv5 / conv6 / deconv1 on 128 x 256 cluster tiles
     "per_thread_store_epilogue": {"SVS_ZC_TMASTORE": "0"},              # zc layers without the TMA-store epilogue
     "weight_multicast_pairs": {"SVS_ZC_MCAST": "1"},                    # CTA pairs share streamed weight chunks (TMA multicast)                     # conv2 / conv3 on 128-byte rows (both concat halves)
 }
