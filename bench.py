@@ -487,7 +487,7 @@ def run_ours(args):
         tc_flops = sum(LAYER_MMAC[li] for li in range(1, 11)) * 2e6 * BATCH
         tc_tflops = tc_flops / (ms_tc * 1e-3) / 1e12
         traffic, traffic_note = None, None
-        for name in ("r02_traffic.json", "r01_traffic.json"):
+        for name in ("r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", name)
             if os.path.exists(tpath):                                 # DRAM bytes of the same kernels from the committed ncu capture
                 with open(tpath) as f:
