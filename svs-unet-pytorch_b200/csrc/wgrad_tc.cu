@@ -245,6 +245,192 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GROUPED form (default).  In wgrad_tc_kernel every tap is its own N = 32 instruction, and each of them re-reads the
+// whole A tile (128 channels x 8 pixels = 4 KB) from shared memory for 1 KB of B: the tensor core's operand fetch,
+// not its arithmetic, sets the pace (measured 41 cycles per instruction against a 16-cycle MMA floor; 14 % tensor-pipe
+// activity in ncu).  In the MN-major layout the N dimension of B is a sequence of 32-channel chunks at a constant
+// pitch (the descriptor's leading byte offset) -- exactly what A's four chunks already are -- so the B tiles of
+// EIGHT TAPS, landed in eight consecutive 8 KB chunks, are ONE N = 256 operand: one instruction per K step multiplies
+// the A tile with eight taps at once and writes accumulator columns [32 tap, 32 tap + 32) for all of them.  Per pass
+// the 13 taps are two groups (8 taps: N = 256, 5 taps: N = 160): 16 instructions per pixel tile instead of 208, and
+// 12 KB of operand fetch per eight taps instead of 40 KB.  Pixel tiles are 64 pixels so that two A tiles (2 x 32 KB)
+// and two tap groups (2 x 64 KB) fit in shared memory.
+constexpr int kGPix = 64;
+constexpr int kGChunk = kGPix * 128;                  // [64 pixels][32 channels] fp32
+constexpr int kGABytes = 4 * kGChunk;
+constexpr int kGASlots = 2;
+constexpr int kGGroupTaps = 8;
+constexpr int kGBSlotBytes = kGGroupTaps * kGChunk;
+constexpr int kGBSlots = 2;
+constexpr size_t kGSmem = static_cast<size_t>(kGASlots) * kGABytes + static_cast<size_t>(kGBSlots) * kGBSlotBytes + 1024 + 256;
+static_assert(kGSmem <= 227 * 1024, "shared memory budget");
+
+__global__ void __launch_bounds__(kWgThreads)
+wgrad_tc_grouped_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_l,
+                        const __grid_constant__ WgParams p) {
+  constexpr int kTaps = 13, kPasses = 2, kN = 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t b_base = smem_base + kGASlots * kGABytes;
+  const size_t bar_off = static_cast<size_t>(kGASlots) * kGABytes + static_cast<size_t>(kGBSlots) * kGBSlotBytes;
+  const uint32_t bar_base = smem_base + static_cast<uint32_t>(bar_off);
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto empty_a = [&](int s) { return bar_base + 8u * (kGASlots + s); };
+  auto full_b = [&](int s) { return bar_base + 8u * (2 * kGASlots + s); };
+  auto empty_b = [&](int s) { return bar_base + 8u * (2 * kGASlots + kGBSlots + s); };
+  const uint32_t acc_full = bar_base + 8u * (2 * kGASlots + 2 * kGBSlots);
+  const uint32_t acc_empty = acc_full + 8u;
+  const uint32_t tmem_slot = acc_full + 16u;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * (2 * kGASlots + 2 * kGBSlots + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x / p.splits, split = blockIdx.x - unit * p.splits;
+  const int mt = unit / p.n_tiles, nt = unit - mt * p.n_tiles;
+  const int per = (p.pix_tiles + p.splits - 1) / p.splits;
+  const int t_begin = split * per, t_end = min(p.pix_tiles, t_begin + per);
+  const int n_my = max(0, t_end - t_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGASlots; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+    for (int s = 0; s < kGBSlots; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_s);
+    tma_prefetch_desc(&tmap_l);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer: per pixel tile the A tile, then the two tap groups of the pass =====
+    int it_a = 0, it_b = 0;
+    for (int pass = 0; pass < kPasses; ++pass) {
+      const int tap0 = pass * (kTaps - 1);
+      for (int i = 0; i < n_my; ++i, ++it_a) {
+        const int tile = t_begin + i;
+        const int tw = tile % p.ntw, th = (tile / p.ntw) % p.nth, tb = tile / (p.ntw * p.nth);
+        const int sa = it_a % kGASlots;
+        mbar_wait(empty_a(sa), ((it_a / kGASlots) & 1) ^ 1);
+        if (elect_one_sync()) {
+          mbar_expect_tx(full_a(sa), kGABytes);
+          for (int c = 0; c < 4; ++c)
+            tma_load_5d(smem_base + sa * kGABytes + c * kGChunk, &tmap_s, full_a(sa), p.s_coff + mt * 128 + c * 32,
+                        tw * p.bw, 0, th * p.bh, tb * p.nb);
+        }
+        __syncwarp();
+        for (int g = 0; g < 2; ++g, ++it_b) {
+          const int first = g * kGGroupTaps, n_t = g == 0 ? kGGroupTaps : kTaps - kGGroupTaps;
+          const int sb = it_b % kGBSlots;
+          mbar_wait(empty_b(sb), ((it_b / kGBSlots) & 1) ^ 1);
+          if (elect_one_sync()) {
+            mbar_expect_tx(full_b(sb), static_cast<uint32_t>(n_t) * kGChunk);
+            for (int t = 0; t < n_t; ++t) {
+              const int tap = tap0 + first + t;
+              const int kh = tap / 5, kw = tap - 5 * kh;
+              const int qh = kh - 2, qw = kw - 2;
+              const int ph = qh & 1, pw = qw & 1;
+              const int dh = (qh - ph) / 2, dw = (qw - pw) / 2;
+              tma_load_5d(b_base + sb * kGBSlotBytes + t * kGChunk, &tmap_l, full_b(sb),
+                          pw * p.l_pitch + p.l_coff + nt * kN, tw * p.bw + dw, ph, th * p.bh + dh, tb * p.nb);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: per pixel tile 2 groups x 8 K steps =====
+    constexpr uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc_g0 = idesc_base | (static_cast<uint32_t>((kGGroupTaps * kN) >> 3) << 17);            // N = 256
+    constexpr uint32_t idesc_g1 = idesc_base | (static_cast<uint32_t>(((kTaps - kGGroupTaps) * kN) >> 3) << 17);  // N = 160
+    int it_a = 0, it_b = 0;
+    for (int pass = 0; pass < kPasses; ++pass) {
+      if (pass > 0) {                                    // the epilogue has drained the accumulators of the last pass
+        mbar_wait(acc_empty, (pass - 1) & 1);
+        tc_fence_after();
+      }
+      for (int i = 0; i < n_my; ++i, ++it_a) {
+        const int sa = it_a % kGASlots;
+        mbar_wait(full_a(sa), (it_a / kGASlots) & 1);
+        tc_fence_after();
+        const uint32_t acc0 = i > 0 ? 1u : 0u;
+        for (int g = 0; g < 2; ++g, ++it_b) {
+          const int sb = it_b % kGBSlots;
+          mbar_wait(full_b(sb), (it_b / kGBSlots) & 1);
+          tc_fence_after();
+          dispatch_stage<0, 8>(sa * 4 + sb * 2 + g, [&](auto sc) {
+            constexpr int SA = decltype(sc)::value >> 2, SB = (decltype(sc)::value >> 1) & 1, G = decltype(sc)::value & 1;
+            const uint64_t da = wg_desc(smem_base + SA * kGABytes, kGChunk);
+            const uint64_t db = wg_desc(smem_base + kGASlots * kGABytes + SB * kGBSlotBytes, kGChunk);
+            const uint32_t tmem_d = tmem_base + G * kGGroupTaps * kN;
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int j = 0; j < kGPix / 8; ++j)      // K step j = pixel rows 8j .. 8j+7: +1024 B on both start addresses
+                umma<true>(tmem_d, da + static_cast<uint64_t>(j * (1024 >> 4)), db + static_cast<uint64_t>(j * (1024 >> 4)),
+                           G == 0 ? idesc_g0 : idesc_g1, j > 0 ? 1u : acc0);
+              umma_commit(bar_base + 8u * (2 * kGASlots + kGBSlots + SB));      // empty_b(SB)
+            }
+            __syncwarp();
+          });
+        }
+        if (elect_one_sync()) umma_commit(empty_a(sa));
+        __syncwarp();
+      }
+      if (elect_one_sync()) umma_commit(acc_full);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: TMEM lane = channel m of S; 13 x 32 columns per pass -> partial[split][tap][m][n] =====
+    const int q = warp & 3;
+    const int r = 32 * q + lane;
+    const int m = mt * 128 + r;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
+    const size_t tap_pitch = static_cast<size_t>(p.s_c) * p.l_c;
+    float* dst0 = p.partial + (static_cast<size_t>(split) * 25 * p.s_c + m) * p.l_c + nt * kN;
+    const int n_valid = min(kN, p.l_c - nt * kN);                // 32, or 16 for the 16-channel layers
+    for (int pass = 0; pass < kPasses; ++pass) {
+      const int tap0 = pass * (kTaps - 1);
+      mbar_wait(acc_full, pass & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < kTaps; ++t) {
+        uint32_t v[32];
+        if (n_my > 0) {
+          tmem_ld16(taddr + t * kN, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld16(taddr + t * kN + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = 0u;
+        }
+        if (m < p.s_c) {
+          float4* d4 = reinterpret_cast<float4*>(dst0 + (tap0 + t) * tap_pitch);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (4 * k < n_valid)
+              d4[k] = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]),
+                                  __uint_as_float(v[4 * k + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // grad_w[(m * l_c + n) * 25 + tap] = sum over splits (fixed order) of partial[split][tap][m][n]
 __global__ void __launch_bounds__(256)
 wgrad_tc_finalize_kernel(const float* __restrict__ partial, int splits, int s_c, int l_c, float* __restrict__ grad_w) {
@@ -277,12 +463,19 @@ static int wg_n(int l_c) {
   return (l_c % 64 == 0 && wide) ? 64 : 32;
 }
 
+// SVS_WGRAD_GROUPED=0 selects the one-instruction-per-tap kernel (wgrad_tc_kernel)
+static bool wg_grouped(int l_c) {
+  static const bool on = [] { const char* e = std::getenv("SVS_WGRAD_GROUPED"); return !(e && e[0] == '0'); }();
+  return on && wg_n(l_c) == 32;
+}
+
 static WgGeom wg_geom(int gh, int gw, int batch, int s_c, int l_c) {
   WgGeom g{};
   const int kWgN = wg_n(l_c);
+  const int pix = wg_grouped(l_c) ? kGPix : 128;                 // pixels per tile
   g.bw = gw < 16 ? gw : 16;
-  g.bh = gh < 128 / g.bw ? gh : 128 / g.bw;
-  g.nb = 128 / (g.bw * g.bh);
+  g.bh = gh < pix / g.bw ? gh : pix / g.bw;
+  g.nb = pix / (g.bw * g.bh);
   g.ntw = gw / g.bw; g.nth = gh / g.bh;
   g.pix_tiles = g.ntw * g.nth * ((batch + g.nb - 1) / g.nb);
   g.m_tiles = (s_c + 127) / 128;
@@ -299,9 +492,11 @@ bool wgrad_tc_supported(int gh, int gw, int s_c, int l_c, int s_pitch, int l_pit
   static const bool off = [] { const char* e = std::getenv("SVS_WGRAD_TC_DISABLE"); return e && e[0] == '1'; }();
   if (off) return false;
   const int bw = gw < 16 ? gw : 16;
-  if (128 % bw != 0) return false;
-  const int bh = gh < 128 / bw ? gh : 128 / bw;
-  if (128 % (bw * bh) != 0 || gw % bw != 0 || gh % bh != 0) return false;
+  if (kGPix % bw != 0) return false;                             // both tile sizes (64 / 128 pixels) must decompose
+  for (int pix : {kGPix, 128}) {
+    const int bh = gh < pix / bw ? gh : pix / bw;
+    if (pix % (bw * bh) != 0 || gw % bw != 0 || gh % bh != 0) return false;
+  }
   return s_c % 32 == 0 && l_c % 16 == 0 && s_pitch % 4 == 0 && l_pitch % 4 == 0 && s_coff % 4 == 0 && l_coff % 4 == 0;
 }
 
@@ -348,7 +543,11 @@ int wgrad_tc_launch(const float* S, int s_pitch, int s_coff, int s_c, const floa
   p.s_c = s_c; p.l_c = l_c; p.l_pitch = l_pitch; p.l_coff = l_coff; p.s_coff = s_coff;
   p.partial = partial;
   const int grid = g.m_tiles * g.n_tiles * g.splits;
-  if (wg_n(l_c) == 64) {
+  if (wg_grouped(l_c)) {
+    SVS_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kGSmem)));
+    wgrad_tc_grouped_kernel<<<grid, kWgThreads, kGSmem, st>>>(ts, tl, p);
+  } else if (wg_n(l_c) == 64) {
     SVS_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(WgCfg<64>::kSmem)));
     wgrad_tc_kernel<64><<<grid, kWgThreads, WgCfg<64>::kSmem, st>>>(ts, tl, p);

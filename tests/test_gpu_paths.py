@@ -63,8 +63,10 @@ def test_kernel_variant_matches_oracle(name, tmp_path):
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def test_wide_wgrad_variant_matches_float64(tmp_path):
-    # SVS_WGRAD_N64=1: the four-pass N = 64 form of wgrad_tc_kernel (selected once per process)
+@pytest.mark.parametrize("flag", ["SVS_WGRAD_N64=1", "SVS_WGRAD_GROUPED=0"])
+def test_wgrad_variant_matches_float64(tmp_path, flag):
+    # SVS_WGRAD_N64=1: the four-pass N = 64 form of wgrad_tc_kernel; SVS_WGRAD_GROUPED=0: its two-pass N = 32 form (one
+    # instruction per tap) instead of the default grouped-tap kernel (selected once per process)
     script = tmp_path / "w.py"
     script.write_text("""
 import os, sys, torch
@@ -84,6 +86,6 @@ for (b, gh, gw, cs, cl) in [(3, 16, 8, 64, 64), (8, 8, 2, 256, 128), (2, 32, 16,
     assert err <= 2e-6, err
 print("ok")
 """)
-    env = dict(os.environ, SVS_ROOT=ROOT, SVS_WGRAD_N64="1")
+    env = dict(os.environ, SVS_ROOT=ROOT, **dict([flag.split("=")]))
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
