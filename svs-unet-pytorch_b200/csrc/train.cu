@@ -14,6 +14,7 @@
 //   plan == NULL: exact fp32 on the CUDA-core kernels of conv_direct.cu (parity mode).
 // conv1 (Cin = 1) and deconv6 (Cout = 1) are memory-bound edge layers with CUDA-core kernels in both modes.
 #include "unet_internal.cuh"
+#include <cstdlib>
 #include "tc_ptx.cuh"
 
 #include <new>
@@ -609,10 +610,23 @@ __global__ void __launch_bounds__(256) sum_stage1_kernel(const float* __restrict
   }
   if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
 }
-__global__ void sum_stage2_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+// Fixed-order sum of a warp: lane l adds elements l, l + 32, ... in double, then a shuffle tree (deterministic; one
+// thread walking all n elements serialised ~2,000 dependent L2 loads = 30-55 us per scalar).
+__device__ __forceinline__ double warp_sum_double(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int lo = __shfl_xor_sync(0xffffffffu, __double2loint(v), o);
+    const int hi = __shfl_xor_sync(0xffffffffu, __double2hiint(v), o);
+    v += __hiloint2double(hi, lo);
+  }
+  return v;
+}
+__global__ void __launch_bounds__(32)
+sum_stage2_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
   double s = 0.0;
-  for (int i = 0; i < n; ++i) s += partial[i];
-  *out = static_cast<float>(s * scale);
+  for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
+  s = warp_sum_double(s);
+  if (threadIdx.x == 0) *out = static_cast<float>(s * scale);
 }
 
 // L = mean|m x - v| + mean|(1-m) x - max(x - v, 0)| ; grad wrt m
@@ -644,12 +658,17 @@ l1_loss_kernel(const float* __restrict__ mask, const float* __restrict__ mix, co
   }
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sv[0]; partial[2 * blockIdx.x + 1] = sa[0]; }
 }
-__global__ void l1_loss_finalize_kernel(const float* __restrict__ partial, int blocks, double n, float* __restrict__ out) {
+__global__ void __launch_bounds__(32)
+l1_loss_finalize_kernel(const float* __restrict__ partial, int blocks, double n, float* __restrict__ out) {
   double v = 0.0, a = 0.0;
-  for (int i = 0; i < blocks; ++i) { v += partial[2 * i]; a += partial[2 * i + 1]; }
-  out[1] = static_cast<float>(v / n);
-  out[2] = static_cast<float>(a / n);
-  out[0] = static_cast<float>(v / n + a / n);
+  for (int i = threadIdx.x; i < blocks; i += 32) { v += partial[2 * i]; a += partial[2 * i + 1]; }
+  v = warp_sum_double(v);
+  a = warp_sum_double(a);
+  if (threadIdx.x == 0) {
+    out[1] = static_cast<float>(v / n);
+    out[2] = static_cast<float>(a / n);
+    out[0] = static_cast<float>(v / n + a / n);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -801,6 +820,12 @@ struct svs_train_plan {
   svs::TcLayer dgr[12];       // layers 1..10
   void* d6_weights = nullptr; // deconv6 as taps-as-N GEMM (deconv6_tc.cu), TF32
   CUtensorMap d6_tmap;
+  // Weight gradients run on a side stream forked from / joined back into the caller's stream inside every backward
+  // call (also under graph capture): they only read dz and the saved activations, so they overlap the data-gradient
+  // chain (BatchNorm passes are HBM bound, the wgrad kernel is bound by operand bytes into shared memory).
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork[12] = {};
+  cudaEvent_t ev_join = nullptr;
 };
 
 using namespace svs;
@@ -828,6 +853,13 @@ extern "C" int svs_unet_train_plan_create(void* stream, svs_train_plan** plan_ou
   }
   rc = d6_make_weight_map(plan->d6_weights, true, &plan->d6_tmap);
   if (rc != SVS_OK) { svs_unet_train_plan_destroy(plan); return rc; }
+  bool ok = cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 12; ++i) ok = cudaEventCreateWithFlags(&plan->ev_fork[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    svs_unet_train_plan_destroy(plan);
+    return fail(SVS_ERR_CUDA, "svs_unet_train_plan_create: stream / event creation failed");
+  }
   *plan_out = plan;
   return SVS_OK;
 }
@@ -836,6 +868,9 @@ extern "C" int svs_unet_train_plan_destroy(svs_train_plan* plan) {
   if (!plan) return SVS_OK;
   for (int li = 0; li < 12; ++li) { tc_free_one(plan->fwd[li]); tc_free_one(plan->dgr[li]); }
   if (plan->d6_weights) cudaFree(plan->d6_weights);
+  for (int i = 0; i < 12; ++i) if (plan->ev_fork[i]) cudaEventDestroy(plan->ev_fork[i]);
+  if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+  if (plan->side) cudaStreamDestroy(plan->side);
   delete plan;
   return SVS_OK;
 }
@@ -1040,6 +1075,16 @@ extern "C" int svs_unet_train_backward_layers(const svs_train_plan* plan, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TrainWs w = carve_train(static_cast<char*>(workspace), batch);
   const bool tc = plan != nullptr;
+  static const bool fork_on = [] { const char* e = std::getenv("SVS_TRAIN_FORK"); return !(e && e[0] == '0'); }();
+  cudaStream_t wst = (tc && fork_on && plan->side) ? plan->side : st;      // stream of the weight gradients
+  bool forked = false;
+  auto fork_wgrad = [&](int li) -> int {               // dz of layer li is complete on st: the side stream may read it
+    if (wst == st) return SVS_OK;
+    SVS_CUDA_TRY(cudaEventRecord(plan->ev_fork[li], st));
+    SVS_CUDA_TRY(cudaStreamWaitEvent(wst, plan->ev_fork[li], 0));
+    forked = true;
+    return SVS_OK;
+  };
   // ---- deconv6: sigmoid backward, bias / weight gradient, data gradient into dcat1 (all 32 channels) ----
   // dz6 holds the forward's mask; dz6 <- grad * m (1 - m) in place
   if (last_layer == 11) {
@@ -1048,9 +1093,11 @@ extern "C" int svs_unet_train_backward_layers(const svs_train_plan* plan, const 
     SVS_CHECK_LAUNCH("sigmoid_bwd_kernel");
     sum_stage1_kernel<<<1024, 256, 0, st>>>(w.dz6, n, w.scalar_partial);
     SVS_CHECK_LAUNCH("sum_stage1_kernel");
-    sum_stage2_kernel<<<1, 1, 0, st>>>(w.scalar_partial, 1024, 1.0f, layers[11].grad_bias);
+    sum_stage2_kernel<<<1, 32, 0, st>>>(w.scalar_partial, 1024, 1.0f, layers[11].grad_bias);
     SVS_CHECK_LAUNCH("sum_stage2_kernel");
-    rc = run_wgrad(w, layers[11], 11, batch, w.dz6, 1, 0, w.cat[BUF_CAT1], 32, 0, tc, st);
+    rc = fork_wgrad(11);
+    if (rc != SVS_OK) return rc;
+    rc = run_wgrad(w, layers[11], 11, batch, w.dz6, 1, 0, w.cat[BUF_CAT1], 32, 0, tc, wst);
     if (rc != SVS_OK) return rc;
     const size_t threads = static_cast<size_t>(batch) * 256 * 64 * 8;
     deconv6_dgrad_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(w.dz6, w.w_fwd[11],
@@ -1089,7 +1136,9 @@ extern "C" int svs_unet_train_backward_layers(const svs_train_plan* plan, const 
     // now z[li] holds dz (gradient w.r.t. the conv output)
     const float* X = li == 0 ? mix : w.cat[g.in_buf];
     const int x_pitch = li == 0 ? 1 : kBufGeom[g.in_buf].c;
-    rc = run_wgrad(w, L, li, batch, w.z[li], g.cout, 0, X, x_pitch, g.in_coff, tc, st);
+    rc = fork_wgrad(li);
+    if (rc != SVS_OK) return rc;
+    rc = run_wgrad(w, L, li, batch, w.z[li], g.cout, 0, X, x_pitch, g.in_coff, tc, wst);
     if (rc != SVS_OK) return rc;
     if (li == 0) break;                                            // the mixture needs no gradient
     // data gradient into dcat[in_buf][in_coff .. in_coff + cin): conv dgrad = transposed kernel, deconv dgrad =
@@ -1112,6 +1161,10 @@ extern "C" int svs_unet_train_backward_layers(const svs_train_plan* plan, const 
     }
     if (rc != SVS_OK) return rc;
   }
+  if (forked) {                                        // join: the caller's stream continues after the last wgrad
+    SVS_CUDA_TRY(cudaEventRecord(plan->ev_join, wst));
+    SVS_CUDA_TRY(cudaStreamWaitEvent(st, plan->ev_join, 0));
+  }
   return SVS_OK;
 }
 
@@ -1123,7 +1176,7 @@ extern "C" int svs_l1_masked_loss(const float* mask, const float* mix, const flo
   l1_loss_kernel<<<1024, 256, 0, st>>>(mask, mix, voc, static_cast<size_t>(n), two_term, grad_scale / static_cast<float>(n),
                                        scratch, grad_mask_out);
   SVS_CHECK_LAUNCH("l1_loss_kernel");
-  l1_loss_finalize_kernel<<<1, 1, 0, st>>>(scratch, 1024, static_cast<double>(n), loss_out);
+  l1_loss_finalize_kernel<<<1, 32, 0, st>>>(scratch, 1024, static_cast<double>(n), loss_out);
   SVS_CHECK_LAUNCH("l1_loss_finalize_kernel");
   return SVS_OK;
 }
