@@ -825,7 +825,7 @@ struct svs_train_plan {
   // chain (BatchNorm passes are HBM bound, the wgrad kernel is bound by operand bytes into shared memory).
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork[12] = {};
-  cudaEvent_t ev_join = nullptr;
+  cudaEvent_t ev_join = nullptr, ev_start = nullptr, ev_pack = nullptr;
 };
 
 using namespace svs;
@@ -854,7 +854,9 @@ extern "C" int svs_unet_train_plan_create(void* stream, svs_train_plan** plan_ou
   rc = d6_make_weight_map(plan->d6_weights, true, &plan->d6_tmap);
   if (rc != SVS_OK) { svs_unet_train_plan_destroy(plan); return rc; }
   bool ok = cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&plan->ev_start, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&plan->ev_pack, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 12; ++i) ok = cudaEventCreateWithFlags(&plan->ev_fork[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     svs_unet_train_plan_destroy(plan);
@@ -870,6 +872,8 @@ extern "C" int svs_unet_train_plan_destroy(svs_train_plan* plan) {
   if (plan->d6_weights) cudaFree(plan->d6_weights);
   for (int i = 0; i < 12; ++i) if (plan->ev_fork[i]) cudaEventDestroy(plan->ev_fork[i]);
   if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+  if (plan->ev_start) cudaEventDestroy(plan->ev_start);
+  if (plan->ev_pack) cudaEventDestroy(plan->ev_pack);
   if (plan->side) cudaStreamDestroy(plan->side);
   delete plan;
   return SVS_OK;
@@ -1085,6 +1089,21 @@ extern "C" int svs_unet_train_backward_layers(const svs_train_plan* plan, const 
     forked = true;
     return SVS_OK;
   };
+  // The data-gradient kernels take channel-transposed weights repacked every step: with a side stream all of this
+  // call's layers are packed there first, under the first BatchNorm passes, instead of one by one in front of each dgrad.
+  bool packed_ahead = false;
+  if (wst != st) {
+    SVS_CUDA_TRY(cudaEventRecord(plan->ev_start, st));
+    SVS_CUDA_TRY(cudaStreamWaitEvent(wst, plan->ev_start, 0));
+    for (int li = last_layer < 10 ? last_layer : 10; li >= (first_layer > 1 ? first_layer : 1); --li) {
+      rc = tc_pack_one(const_cast<TcLayer&>(plan->dgr[li]), w.w_t[li], true, wst);
+      if (rc != SVS_OK) return rc;
+    }
+    SVS_CUDA_TRY(cudaEventRecord(plan->ev_pack, wst));
+    forked = true;
+    packed_ahead = true;
+  }
+  bool pack_waited = false;
   // ---- deconv6: sigmoid backward, bias / weight gradient, data gradient into dcat1 (all 32 channels) ----
   // dz6 holds the forward's mask; dz6 <- grad * m (1 - m) in place
   if (last_layer == 11) {
@@ -1147,8 +1166,13 @@ extern "C" int svs_unet_train_backward_layers(const svs_train_plan* plan, const 
     const bool accumulate = !g.transposed;
     if (tc) {
       TcLayer& t = const_cast<TcLayer&>(plan->dgr[li]);
-      rc = tc_pack_one(t, w.w_t[li], true, st);
-      if (rc != SVS_OK) return rc;
+      if (!packed_ahead) {
+        rc = tc_pack_one(t, w.w_t[li], true, st);
+        if (rc != SVS_OK) return rc;
+      } else if (!pack_waited) {
+        SVS_CUDA_TRY(cudaStreamWaitEvent(st, plan->ev_pack, 0));
+        pack_waited = true;
+      }
       TcIo io;
       io.in = w.z[li]; io.out = w.dcat[g.in_buf]; io.bias = w.zero_bias;
       io.splitk = w.splitk; io.splitk_bytes = w.splitk_bytes;
