@@ -363,21 +363,25 @@ class UNetPlan:
     def workspace(self, batch: int) -> torch.Tensor:
         """Activation workspace for `batch` patches on the CURRENT stream.  svs_unet_forward writes every concat
         buffer into it, so two forwards in flight on different streams must not share one: the cache is keyed by
-        stream (each stream keeps the workspace of its last batch size).  A workspace is only ever used on the
-        stream it was allocated under, so dropping it hands the block back to the caching allocator's pool of that
-        same stream and any re-use is stream-ordered after the kernels that still read it."""
-        key = torch.cuda.current_stream(self.device).cuda_stream
-        hit = self._ws.get(key)
-        if hit is not None and hit[0] == batch:
-            return hit[1]
-        nbytes = load().svs_unet_workspace_bytes(self.handle, batch)
-        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
-        off = (-raw.data_ptr()) % 1024
-        ws = raw[off:off + nbytes]
-        if hit is None and len(self._ws) >= 16:                       # bound the number of per-stream workspaces
-            self._ws.pop(next(iter(self._ws)))
-        self._ws[key] = (batch, ws)
-        return ws
+        (stream, batch).  A stream keeps the workspaces of its last few batch sizes (a corpus whose last batch is
+        ragged alternates between two sizes: re-allocating on every switch cost the 19-song shard of the 8-GPU run
+        two allocator round trips per pass).  A workspace is only ever used on the stream it was allocated under, so
+        dropping it hands the block back to the caching allocator's pool of that same stream and any re-use is
+        stream-ordered after the kernels that still read it."""
+        key = (torch.cuda.current_stream(self.device).cuda_stream, batch)
+        hit = self._ws.pop(key, None)
+        if hit is None:
+            nbytes = load().svs_unet_workspace_bytes(self.handle, batch)
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-raw.data_ptr()) % 1024
+            hit = raw[off:off + nbytes]
+            per_stream = [k for k in self._ws if k[0] == key[0]]
+            if len(per_stream) >= 3:                                     # keep at most three more sizes per stream
+                self._ws.pop(per_stream[0])
+            while len(self._ws) >= 32:                                   # and bound the whole cache
+                self._ws.pop(next(iter(self._ws)))
+        self._ws[key] = hit                                              # most recently used last
+        return hit
 
     def launch_count(self, batch: int) -> int:
         return load().svs_unet_launch_count(self.handle, batch)
