@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SVS_ABI_VERSION 2
+#define SVS_ABI_VERSION 3   /* 3: + svs_patch_stream_* (host-buffer patch batches) */
 
 /* geometry of the path (reference config.py:47-51) */
 #define SVS_N_FFT        1024

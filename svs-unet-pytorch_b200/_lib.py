@@ -19,7 +19,7 @@ FLAG_APPLY_MASK = 1
 FLAG_INVERT = 2
 
 N_FFT, HOP, N_BINS, PATCH_BINS, PATCH_FRAMES = 1024, 768, 513, 512, 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 L1_SCRATCH_FLOATS = 2048
 
 

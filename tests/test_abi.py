@@ -26,7 +26,7 @@ def test_header_symbols_exported():
 def test_version_and_error_string():
     from svs_unet_pytorch_b200 import _lib
     lib = _lib.load()
-    assert lib.svs_version() == 2
+    assert lib.svs_version() == _lib.ABI_VERSION == 3
     assert isinstance(lib.svs_last_error(), (bytes, type(None)))
 
 
