@@ -477,6 +477,10 @@ def run_ours(args):
                  "allreduce_exposed_ms": max(0.0, ms_tr - ms_tr_local) if world > 1 else 0.0,
                  "allreduce_payload_bytes": 9823313 * 4 if world > 1 else 0,
                  "precision": training.train_precision(tnet), "cuda_graph": True}
+        if tf32 is not None:                                          # forward + dgrad + wgrad FLOPs against the TF32 peak
+            train["roofline"] = {"bound": "tensor", "achieved": train["tflops_exact"], "peak": tf32["roofline"]["peak"],
+                                 "unit": "TFLOP/s", "frac": train["tflops_exact"] / tf32["roofline"]["peak"],
+                                 "note": "whole step incl. BatchNorm passes, loss and Adam; 3.961 GFLOP/patch exact"}
         del tnet, tmix, tvoc
 
     if rank == 0:
