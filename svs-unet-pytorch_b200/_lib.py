@@ -210,11 +210,14 @@ def istft_ola_raw(mag, phase, frame_off, wave_off, n_songs, max_frames, total_sa
     require_cuda(phase, "phase", torch.float32)
     check_device(mag.device)
     dev = mag.device
-    wave = torch.empty((max(total_samples, 1),), dtype=torch.float32, device=dev)[:total_samples]
+    # single-frame songs have hop * (T - 1) = 0 output samples (librosa returns an empty array): a batch of them has an
+    # empty waveform, whose data_ptr() is null -- pass the one-element backing store instead
+    base = torch.empty((max(total_samples, 1),), dtype=torch.float32, device=dev)
+    wave = base[:total_samples]
     peak = torch.empty((n_songs,), dtype=torch.float32, device=dev) if want_peak else None
     with torch.cuda.device(dev):
         check(load().svs_istft_ola(mag.data_ptr(), phase.data_ptr(), frame_off.data_ptr(), wave_off.data_ptr(),
-                                   n_songs, max_frames, wave.data_ptr(),
+                                   n_songs, max_frames, base.data_ptr(),
                                    peak.data_ptr() if peak is not None else None, stream_ptr(dev)),
               "svs_istft_ola")
     return wave, peak

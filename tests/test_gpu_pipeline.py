@@ -133,6 +133,13 @@ def test_host_streamer_matches_direct_forward():
         assert torch.equal(b, hout[i])
     with pytest.raises(Exception):
         st.run([torch.rand(3, 1, 512, 128)], [torch.empty(3, 1, 512, 128)])     # wrong batch: rejected, not truncated
+    # the minimum staging depth (two slots): every upload waits for the forward two steps back
+    st2 = pipeline.PatchStreamer(net, batch=4, vocal_solo=True, n_buf=2)
+    hout3 = [torch.zeros(4, 1, 512, 128).pin_memory() for _ in range(7)]
+    st2.run([hin[i % 5] for i in range(7)], hout3)
+    torch.cuda.synchronize()
+    for i, b in enumerate(hout3):
+        assert torch.equal(b, hout[i % 5])
 
 
 @pytest.mark.parametrize("precision,tol", [("bf16", 1e-2), ("tf32", 1e-3)])

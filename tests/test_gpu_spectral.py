@@ -165,3 +165,26 @@ def test_gpu_resampler_matches_scipy_polyphase_oracle():
     y = resample.resample(x, 48000, 8192)
     ref = resample_oracle.load_like(x, 48000, 8192)
     assert y.shape == ref.shape and np.abs(y - ref).max() <= 2e-6
+
+
+@pytest.mark.parametrize("n_songs,seed", [(1, 0), (7, 1), (97, 2), (300, 3)])
+def test_istft_ragged_batch_equals_song_by_song(n_songs, seed):
+    # The iSTFT splits the batch's frames evenly over a one-wave grid, in runs that cross song borders (istft.cu).  A
+    # frame's arithmetic does not depend on where the runs are cut, so a ragged batch must reproduce, BIT FOR BIT, what
+    # each song gives alone -- from one-frame songs up to batches with more songs than CTAs.
+    rng = np.random.default_rng(seed)
+    lengths = rng.integers(1, 768 * 40, size=n_songs)
+    lengths[rng.integers(0, n_songs)] = 700                           # a single-frame song somewhere
+    songs = [(0.2 * rng.standard_normal(int(n))).astype(np.float32) for n in lengths]
+    batch = spectral.SongBatch.from_audio(songs)
+    mag, phase, _ = batch.stft()
+    wave, peak = batch.istft(mag, phase)
+    torch.cuda.synchronize()
+    for i in rng.permutation(n_songs)[:12]:
+        one = spectral.SongBatch.from_audio([songs[i]])
+        m1, p1, _ = one.stft()
+        w1, k1 = one.istft(m1, p1)
+        assert torch.equal(batch.song_spec(mag, i), one.song_spec(m1, 0))
+        got = batch.song_wave(wave, i)
+        assert got.numel() == one.wave_lengths[0] and torch.equal(got, one.song_wave(w1, 0))
+        assert float(peak[i]) == float(k1[0])
