@@ -452,6 +452,40 @@ wgrad_tc_finalize_kernel(const float* __restrict__ partial, int splits, int s_c,
   }
 }
 
+// The same sum for layers with MANY splits and few outputs (the shallow layers: one or two work units, 74-148 splits).
+// A CTA finishes 32 consecutive outputs: thread (group g of 8, output o) adds the splits k = g, g + 8, ... and the
+// eight group sums are combined in shared memory in fixed order (deterministic, no atomics).  One thread per output
+// walking all ~148 splits left a 50-CTA grid waiting on ~37 dependent L2 round trips (23-30 us per layer).
+constexpr int kWgFinGroups = 8;
+__global__ void __launch_bounds__(256)
+wgrad_tc_finalize_many_kernel(const float* __restrict__ partial, int splits, int s_c, int l_c, float* __restrict__ grad_w) {
+  __shared__ float red[kWgFinGroups][32];
+  const int total = 25 * s_c * l_c;
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+    const int i = base + o;
+    float s0 = 0.f, s1 = 0.f;
+    if (i < total) {
+      int k = g;
+      for (; k + kWgFinGroups < splits; k += 2 * kWgFinGroups) {
+        s0 += partial[static_cast<size_t>(k) * total + i];
+        s1 += partial[static_cast<size_t>(k + kWgFinGroups) * total + i];
+      }
+      if (k < splits) s0 += partial[static_cast<size_t>(k) * total + i];
+    }
+    red[g][o] = s0 + s1;
+    __syncthreads();
+    if (g == 0 && i < total) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < kWgFinGroups; ++q) s += red[q][o];
+      const int n = i % l_c, m = (i / l_c) % s_c, tap = i / (l_c * s_c);
+      grad_w[(static_cast<size_t>(m) * l_c + n) * 25 + tap] = s;
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host
 struct WgGeom { int bw, bh, nb, ntw, nth, pix_tiles, m_tiles, n_tiles, splits; };
@@ -558,9 +592,15 @@ int wgrad_tc_launch(const float* S, int s_pitch, int s_coff, int s_c, const floa
   }
   SVS_CHECK_LAUNCH("wgrad_tc_kernel");
   const int total = 25 * s_c * l_c;
-  int blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_tc_finalize_kernel<<<blocks, 256, 0, st>>>(partial, g.splits, s_c, l_c, grad_w);
+  if (g.splits >= 32) {                              // many splits, few outputs: 8 split groups per output
+    int blocks = (total + 31) / 32;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_tc_finalize_many_kernel<<<blocks, 256, 0, st>>>(partial, g.splits, s_c, l_c, grad_w);
+  } else {
+    int blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_tc_finalize_kernel<<<blocks, 256, 0, st>>>(partial, g.splits, s_c, l_c, grad_w);
+  }
   SVS_CHECK_LAUNCH("wgrad_tc_finalize_kernel");
   return SVS_OK;
 }
