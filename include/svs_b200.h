@@ -253,8 +253,10 @@ typedef struct svs_train_layer {
  * forward, data-gradient and weight-gradient convolutions — what torch + cuDNN do by default for the reference's
  * fp32 model on a GPU (torch.backends.cudnn.allow_tf32) — while BatchNorm statistics, normalisation, the loss and every
  * reduction stay fp32.  plan == NULL runs the whole step in exact fp32 on CUDA cores (parity mode).  The plan owns
- * only device scratch for repacked weights (rewritten by every forward call); it holds no parameters and may be
- * shared by successive steps, not by concurrent ones. */
+ * device scratch for repacked weights (rewritten by every forward call) and one internal side stream: every backward
+ * call forks the weight gradients and the data-gradient weight packing onto it and joins it back into the caller's
+ * stream before returning (also under CUDA-graph capture), so all of a call's work is ordered on the caller's stream
+ * as usual.  The plan holds no parameters and may be shared by successive steps, not by concurrent ones. */
 typedef struct svs_train_plan svs_train_plan;
 int svs_unet_train_plan_create(void* stream, svs_train_plan** plan_out);
 int svs_unet_train_plan_destroy(svs_train_plan* plan);

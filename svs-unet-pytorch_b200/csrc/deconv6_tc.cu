@@ -126,7 +126,9 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int n = pr & 63, oyl = pr >> 6;
       const int oy = 2 * (row0 + 1 + (oyl >> 1)) + (oyl & 1);
       float2 v = make_float2(1.0f, 1.0f);
-      if ((flags & SVS_FLAG_APPLY_MASK) && oy < 512) v = __ldg(reinterpret_cast<const float2*>(mix_b + oy * 128 + 2 * n));
+      // the mixture and the result are touched once per forward: streaming accesses keep them from evicting the
+      // skip activations that are still waiting in L2
+      if ((flags & SVS_FLAG_APPLY_MASK) && oy < 512) v = __ldcs(reinterpret_cast<const float2*>(mix_b + oy * 128 + 2 * n));
       mixv[2 * j] = v.x; mixv[2 * j + 1] = v.y;
     }
   } else {
@@ -194,7 +196,7 @@ deconv6_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (flags & SVS_FLAG_INVERT) { m0 = 1.0f - m0; m1 = 1.0f - m1; } // inference.py:102
       float* dst = out_b + oy * 128 + 2 * n;
       // inference.py:107 (mixv = 1 without APPLY_MASK); frames >= nf are cropped (inference.py:113)
-      if (2 * n + 1 < nf) *reinterpret_cast<float2*>(dst) = make_float2(m0 * mixv[2 * j], m1 * mixv[2 * j + 1]);
+      if (2 * n + 1 < nf) __stcs(reinterpret_cast<float2*>(dst), make_float2(m0 * mixv[2 * j], m1 * mixv[2 * j + 1]));
       else if (2 * n < nf) dst[0] = m0 * mixv[2 * j];
     }
   } else {
