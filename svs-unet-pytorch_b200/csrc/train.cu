@@ -484,51 +484,54 @@ wgrad_small_kernel(WgradArgs a, int gw_log2, int gh_log2, int sc_log2, int lc_lo
 // (broadcast).  Every CTA writes one partial [25][C]; wgrad_edge_finalize_kernel adds them in fixed order.  Memory
 // bound (S is read once: 67 / 134 MB per 64 patches) instead of the 25 x re-read of wgrad_small_kernel.
 constexpr int kEdgeRows = 8;
+// Thread = (channel c, kernel row kh): warp kh of the 160-thread CTA holds the five kw taps of its row in registers
+// and slides a five-sample window of L along x (two new samples per step, broadcast to all lanes); S is read straight
+// from global memory, one coalesced 128-byte line per warp and step.  1 LDG + 2 LDS + 5 FFMA per step and no barrier
+// inside the row loop (the round-2a form staged every S row through shared memory behind two barriers and spent 9
+// instructions per 4 FFMA: 182 / 115 us per step for deconv6 / conv1).  C = 16: the two half-warps take the two halves
+// of a row and are combined by one shuffle at the end.
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(160)
 wgrad_edge_kernel(const float* __restrict__ S /*[B][256][64][C]*/, const float* __restrict__ L /*[B][512][128]*/,
                   float* __restrict__ partial /*[gridDim.y * gridDim.x][25][C]*/) {
-  constexpr int kGroups = 256 / C;                       // tap groups: 8 (C = 32) or 16 (C = 16)
-  constexpr int kTaps = (25 + kGroups - 1) / kGroups;    // taps per thread: 4 or 2
+  constexpr int kHalves = 32 / C;                        // lane groups along x: 1 (C = 32) or 2 (C = 16)
+  constexpr int kXs = 64 / kHalves;                      // steps per row and lane
   constexpr int kWinW = 132, kWinH = 2 * kEdgeRows + 3;
   __shared__ float win[kWinH * kWinW];
-  __shared__ __align__(16) float srow[64 * C];
   const int b = blockIdx.y, row0 = blockIdx.x * kEdgeRows;
   const float* Lb = L + static_cast<size_t>(b) * 512 * 128;
-  for (int i = threadIdx.x; i < kWinH * kWinW; i += 256) {
+  for (int i = threadIdx.x; i < kWinH * kWinW; i += 160) {
     const int r = i / kWinW, c = i - r * kWinW;
     const int ly = 2 * row0 - 2 + r, lx = c - 2;
     win[i] = (ly >= 0 && ly < 512 && lx >= 0 && lx < 128 && c < 131) ? __ldg(Lb + ly * 128 + lx) : 0.0f;
   }
-  const int c = threadIdx.x % C, tg = threadIdx.x / C;
-  int off[kTaps];
-  float acc[kTaps];
-#pragma unroll
-  for (int k = 0; k < kTaps; ++k) {
-    const int tap = tg + k * kGroups;
-    off[k] = tap < 25 ? (tap / 5) * kWinW + tap % 5 : -1;
-    acc[k] = 0.0f;
-  }
-  const float* Sb = S + (static_cast<size_t>(b) * 256 + row0) * 64 * C;
+  __syncthreads();
+  const int kh = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = lane % C, xh = lane / C;
+  const int x0 = xh * kXs;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* Sb = S + (static_cast<size_t>(b) * 256 + row0) * 64 * C + c;
   for (int r = 0; r < kEdgeRows; ++r) {
-    __syncthreads();                                     // window ready / previous row consumed
-    const float4* src = reinterpret_cast<const float4*>(Sb + static_cast<size_t>(r) * 64 * C);
-    for (int i = threadIdx.x; i < 64 * C / 4; i += 256) reinterpret_cast<float4*>(srow)[i] = __ldg(src + i);
-    __syncthreads();
-    const float* wrow = win + 2 * r * kWinW;
+    const float* wrow = win + (2 * r + kh) * kWinW + 2 * x0;       // sample 2x + kw - 2 sits at window column 2x + kw
+    const float* srow = Sb + (static_cast<size_t>(r) * 64 + x0) * C;
+    float l0 = wrow[0], l1 = wrow[1], l2 = wrow[2];
 #pragma unroll 8
-    for (int x = 0; x < 64; ++x) {
-      const float s = srow[x * C + c];
-#pragma unroll
-      for (int k = 0; k < kTaps; ++k)
-        if (off[k] >= 0) acc[k] = fmaf(s, wrow[off[k] + 2 * x], acc[k]);
+    for (int x = 0; x < kXs; ++x) {
+      const float s = __ldg(srow + x * C);
+      const float l3 = wrow[2 * x + 3], l4 = wrow[2 * x + 4];
+      acc[0] = fmaf(s, l0, acc[0]); acc[1] = fmaf(s, l1, acc[1]); acc[2] = fmaf(s, l2, acc[2]);
+      acc[3] = fmaf(s, l3, acc[3]); acc[4] = fmaf(s, l4, acc[4]);
+      l0 = l2; l1 = l3; l2 = l4;
     }
   }
-  float* dst = partial + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 25 * C;
+  if (kHalves == 2) {
 #pragma unroll
-  for (int k = 0; k < kTaps; ++k) {
-    const int tap = tg + k * kGroups;
-    if (tap < 25) dst[tap * C + c] = acc[k];
+    for (int k = 0; k < 5; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+  }
+  float* dst = partial + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 25 * C;
+  if (xh == 0) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dst[(kh * 5 + k) * C + c] = acc[k];
   }
 }
 
@@ -1041,8 +1044,8 @@ static int run_wgrad(const TrainWs& w, const svs_train_layer& L, int li, int bat
     const int C = li == 0 ? 16 : 32;
     if (w.wgrad_partial_floats < static_cast<size_t>(n_partials) * 25 * C)
       return fail(SVS_ERR_WORKSPACE, "run_wgrad: partial buffer too small");
-    if (li == 0) wgrad_edge_kernel<16><<<grid, 256, 0, st>>>(S, Lt, w.wgrad_partial);
-    else wgrad_edge_kernel<32><<<grid, 256, 0, st>>>(S, Lt, w.wgrad_partial);
+    if (li == 0) wgrad_edge_kernel<16><<<grid, 160, 0, st>>>(S, Lt, w.wgrad_partial);
+    else wgrad_edge_kernel<32><<<grid, 160, 0, st>>>(S, Lt, w.wgrad_partial);
     SVS_CHECK_LAUNCH("wgrad_edge_kernel");
     wgrad_edge_finalize_kernel<<<(25 * C * 32 + 127) / 128, 128, 0, st>>>(w.wgrad_partial, n_partials, C, L.grad_weight);
     SVS_CHECK_LAUNCH("wgrad_edge_finalize_kernel");
