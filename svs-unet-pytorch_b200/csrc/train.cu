@@ -575,36 +575,39 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ mask, const float* 
 // channels and walks the 25 taps in (kh, kw) order: 4 LDS + 2 broadcast LDS.128 + 32 FFMA per tap, ~30 instructions
 // per output against ~70 for the thread-per-(pixel, 4 channels) form with its redundant, branchy global loads
 // (142 -> ~45 us per 64-patch step).
-constexpr int kD6dRows = 4;                           // input rows per CTA
-constexpr int kD6dWin = 2 * kD6dRows + 3;             // dz rows 2 ih0 - 2 .. 2 ih0 + 2 kD6dRows
+// The same kernel is conv1's training forward (1 -> 16 channels, + bias): C = 16 gives 8 rows per CTA.
 constexpr int kD6dPitch = 128 + 4;                    // 2 zero columns each side
+template <int C, bool kBias>
 __global__ void __launch_bounds__(256)
-deconv6_dgrad_kernel(const float* __restrict__ dz /*[B][512][128]*/, const float* __restrict__ w /*[25][32]*/,
-                     float* __restrict__ dx /*[B][256][64][32]*/, int batch) {
-  __shared__ __align__(16) float sw[25 * 32];
-  __shared__ float sdz[kD6dWin * kD6dPitch];
-  const int b = blockIdx.y, ih0 = blockIdx.x * kD6dRows;
-  for (int i = threadIdx.x; i < 800; i += 256) sw[i] = w[i];
-  for (int i = threadIdx.x; i < kD6dWin * kD6dPitch; i += 256) {
+edge_conv_kernel(const float* __restrict__ dz /*[B][512][128]*/, const float* __restrict__ w /*[25][C]*/,
+                 const float* __restrict__ bias /*[C] or null*/, float* __restrict__ dx /*[B][256][64][C]*/, int batch) {
+  constexpr int kGroups = C / 8;                      // 8-channel groups
+  constexpr int kRows = 256 / (16 * kGroups);         // small-grid rows per CTA: 4 (C = 32) or 8 (C = 16)
+  constexpr int kWin = 2 * kRows + 3;                 // image rows 2 ih0 - 2 .. 2 ih0 + 2 kRows
+  __shared__ __align__(16) float sw[25 * C];
+  __shared__ float sdz[kWin * kD6dPitch];
+  const int b = blockIdx.y, ih0 = blockIdx.x * kRows;
+  for (int i = threadIdx.x; i < 25 * C; i += 256) sw[i] = w[i];
+  for (int i = threadIdx.x; i < kWin * kD6dPitch; i += 256) {
     const int r = i / kD6dPitch, c = i - r * kD6dPitch - 2;
     const int oh = 2 * ih0 - 2 + r;
     sdz[i] = (oh >= 0 && oh < 512 && c >= 0 && c < 128) ? dz[(static_cast<size_t>(b) * 512 + oh) * 128 + c] : 0.0f;
   }
   __syncthreads();
-  const int cg = threadIdx.x >> 6;                    // 8-channel group: uniform within a warp (weights broadcast)
-  const int row = (threadIdx.x >> 4) & 3, pxg = threadIdx.x & 15;
+  const int cg = threadIdx.x / (16 * kRows);          // 8-channel group: uniform within a warp (weights broadcast)
+  const int row = (threadIdx.x >> 4) % kRows, pxg = threadIdx.x & 15;
   float acc[4][8];
 #pragma unroll
   for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc[k][u] = 0.0f;
+    for (int u = 0; u < 8; ++u) acc[k][u] = kBias ? bias[8 * cg + u] : 0.0f;
 #pragma unroll
   for (int kh = 0; kh < 5; ++kh) {
     const float* drow = sdz + (2 * row + kh) * kD6dPitch + 2 * pxg;   // column 2 iw - 2 + kw + 2 (border) = 2 iw + kw
 #pragma unroll
     for (int kw = 0; kw < 5; ++kw) {
-      const float4 w0 = *reinterpret_cast<const float4*>(sw + (kh * 5 + kw) * 32 + 8 * cg);
-      const float4 w1 = *reinterpret_cast<const float4*>(sw + (kh * 5 + kw) * 32 + 8 * cg + 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + (kh * 5 + kw) * C + 8 * cg);
+      const float4 w1 = *reinterpret_cast<const float4*>(sw + (kh * 5 + kw) * C + 8 * cg + 4);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float g = drow[32 * k + kw];             // pixel iw = pxg + 16 k
@@ -618,7 +621,7 @@ deconv6_dgrad_kernel(const float* __restrict__ dz /*[B][512][128]*/, const float
   const size_t pix0 = (static_cast<size_t>(b) * 256 + ih0 + row) * 64;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    float4* dst = reinterpret_cast<float4*>(dx + (pix0 + pxg + 16 * k) * 32 + 8 * cg);
+    float4* dst = reinterpret_cast<float4*>(dx + (pix0 + pxg + 16 * k) * C + 8 * cg);
     dst[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
     dst[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
   }
@@ -989,7 +992,9 @@ extern "C" int svs_unet_train_forward(const svs_train_plan* plan, const svs_trai
       break;
     }
     if (li == 0) {
-      rc = launch_conv1_f32(mix, w.w_fwd[0], L.bias, w.z[0], batch, st);
+      edge_conv_kernel<16, true><<<dim3(256 / 8, batch), 256, 0, st>>>(mix, w.w_fwd[0], L.bias, w.z[0], batch);
+      SVS_CHECK_LAUNCH("edge_conv_kernel");
+      rc = SVS_OK;
     } else if (tc) {
       TcLayer& t = const_cast<TcLayer&>(plan->fwd[li]);            // the plan owns only packed weights: rewritten per step
       rc = tc_pack_one(t, w.w_fwd[li], true, st);
@@ -1147,8 +1152,8 @@ extern "C" int svs_unet_train_backward_layers(const svs_train_plan* plan, const 
     if (rc != SVS_OK) return rc;
     rc = run_wgrad(w, layers[11], 11, batch, w.dz6, 1, 0, w.cat[BUF_CAT1], 32, 0, tc, wst);
     if (rc != SVS_OK) return rc;
-    deconv6_dgrad_kernel<<<dim3(256 / kD6dRows, batch), 256, 0, st>>>(w.dz6, w.w_fwd[11], w.dcat[BUF_CAT1], batch);
-    SVS_CHECK_LAUNCH("deconv6_dgrad_kernel");
+    edge_conv_kernel<32, false><<<dim3(256 / 4, batch), 256, 0, st>>>(w.dz6, w.w_fwd[11], nullptr, w.dcat[BUF_CAT1], batch);
+    SVS_CHECK_LAUNCH("edge_conv_kernel");
   }
   // ---- deconv5 .. deconv1, conv6 .. conv1 ----
   for (int li = last_layer < 10 ? last_layer : 10; li >= first_layer; --li) {
