@@ -846,8 +846,18 @@ static ConvDesc train_fwd_desc(int li) {
 
 }  // namespace svs
 
+namespace svs {
+int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st);
+int zc_repack_layer(svs_unet_plan* plan, int li, const float* w_fold, cudaStream_t st);
+int zc_launch_layer_io(const svs_unet_plan* plan, int li, const ZcIo& io, int batch, cudaStream_t st);
+void zc_free_layers(svs_unet_plan* plan);
+}  // namespace svs
+
 struct svs_train_plan {
   int device = 0;
+  // The zero-copy implicit-GEMM kernels of the inference path (zc_conv.cu, TF32 form) for the FORWARD of conv2-4 and
+  // deconv3-5: `zcp` is an inference-plan shell that only carries their ZcLayer state (weights repacked per step).
+  svs_unet_plan zcp;
   svs::TcLayer fwd[12];       // layers 1..10
   svs::TcLayer dgr[12];       // layers 1..10
   void* d6_weights = nullptr; // deconv6 as taps-as-N GEMM (deconv6_tc.cu), TF32
@@ -879,6 +889,17 @@ extern "C" int svs_unet_train_plan_create(void* stream, svs_train_plan** plan_ou
       rc = fail(SVS_ERR_NOT_IMPLEMENTED, "svs_unet_train_plan_create: no tcgen05 mapping for layer " + std::to_string(li));
     if (rc != SVS_OK) { svs_unet_train_plan_destroy(plan); return rc; }
   }
+  plan->zcp.precision = SVS_PRECISION_TF32;
+  plan->zcp.elem_size = 4;
+  plan->zcp.device = dev;
+  {
+    static const bool zc_on = [] { const char* e = std::getenv("SVS_TRAIN_ZC"); return !(e && e[0] == '0'); }();
+    for (int li : {1, 2, 3, 8, 9, 10}) {
+      if (!zc_on) break;
+      rc = zc_plan_layer(&plan->zcp, li, st);          // w_fold == nullptr: geometry, buffers and tensor maps only
+      if (rc != SVS_OK) { svs_unet_train_plan_destroy(plan); return rc; }
+    }
+  }
   if (cudaMalloc(&plan->d6_weights, 32 * 32 * sizeof(float)) != cudaSuccess) {
     svs_unet_train_plan_destroy(plan);
     return fail(SVS_ERR_CUDA, "svs_unet_train_plan_create: cudaMalloc failed");
@@ -901,6 +922,7 @@ extern "C" int svs_unet_train_plan_create(void* stream, svs_train_plan** plan_ou
 extern "C" int svs_unet_train_plan_destroy(svs_train_plan* plan) {
   if (!plan) return SVS_OK;
   for (int li = 0; li < 12; ++li) { tc_free_one(plan->fwd[li]); tc_free_one(plan->dgr[li]); }
+  zc_free_layers(&plan->zcp);
   if (plan->d6_weights) cudaFree(plan->d6_weights);
   for (int i = 0; i < 12; ++i) if (plan->ev_fork[i]) cudaEventDestroy(plan->ev_fork[i]);
   if (plan->ev_join) cudaEventDestroy(plan->ev_join);
@@ -995,6 +1017,14 @@ extern "C" int svs_unet_train_forward(const svs_train_plan* plan, const svs_trai
       edge_conv_kernel<16, true><<<dim3(256 / 8, batch), 256, 0, st>>>(mix, w.w_fwd[0], L.bias, w.z[0], batch);
       SVS_CHECK_LAUNCH("edge_conv_kernel");
       rc = SVS_OK;
+    } else if (tc && plan->zcp.zc[li].enabled) {
+      svs_unet_plan* zp = const_cast<svs_unet_plan*>(&plan->zcp);  // zero-copy kernel: halo slab landed once per tile
+      rc = zc_repack_layer(zp, li, w.w_fwd[li], st);
+      if (rc != SVS_OK) return rc;
+      ZcIo io;
+      io.in = w.cat[g.in_buf]; io.out = w.z[li]; io.out_pitch = g.cout; io.out_coff = 0;
+      io.bias = L.bias; io.act = ACT_NONE; io.keep_fp32 = 1; io.wait_first = 1;
+      rc = zc_launch_layer_io(zp, li, io, batch, st);
     } else if (tc) {
       TcLayer& t = const_cast<TcLayer&>(plan->fwd[li]);            // the plan owns only packed weights: rewritten per step
       rc = tc_pack_one(t, w.w_fwd[li], true, st);

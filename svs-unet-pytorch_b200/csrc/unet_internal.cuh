@@ -152,6 +152,17 @@ struct ZcLayer {
   CUtensorMap tmap_b_quarter;        // box of n_total / 4 rows: one sub-pixel phase block of a merged deconv chunk
 };
 
+// buffers / epilogue of one zero-copy launch (zc_launch_layer_io)
+struct ZcIo {
+  const void* in = nullptr;
+  void* out = nullptr;
+  int out_pitch = 0, out_coff = 0;
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  int keep_fp32 = 0;                 // fp32 outputs unrounded
+  int wait_first = 0;                // weights are repacked in-stream: wait for the previous grid before preloading them
+};
+
 }  // namespace svs
 
 struct svs_unet_plan {

@@ -28,6 +28,7 @@ namespace svs {
 
 extern long long* g_tc_dbg;
 extern int g_tc_dbg_layer;
+int zc_launch_layer_io(const svs_unet_plan* plan, int li, const ZcIo& io, int batch, cudaStream_t st);
 
 constexpr int kZcThreads = 192;
 constexpr int kZcBw = 8, kZcBh = 16;                 // M tile: 16 image rows x 8 pixels
@@ -47,6 +48,8 @@ struct ZcParams {
   const float* bias;
   int cout_phase, merged, act;
   int resident;                  // weights resident in smem
+  int keep_fp32;                 // fp32 outputs are NOT rounded to TF32 (training: pre-BatchNorm z)
+  int wait_first;                // griddepcontrol.wait before the resident-weight preload (weights repacked per step)
   long long* dbg;                // profiling: per CTA 64 clock64 stamps
 };
 
@@ -71,11 +74,14 @@ __device__ __forceinline__ void zc_store16(__nv_bfloat16* dst, const float (&f)[
   reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
   reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
-__device__ __forceinline__ void zc_store16(float* dst, const float (&f)[16]) {   // fp32 activations feed kind::tf32
+__device__ __forceinline__ void zc_store16(float* dst, const float (&f)[16], int keep_fp32 = 0) {   // fp32 activations feed kind::tf32
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    reinterpret_cast<float4*>(dst)[i] = make_float4(round_tf32(f[4 * i]), round_tf32(f[4 * i + 1]), round_tf32(f[4 * i + 2]), round_tf32(f[4 * i + 3]));
+    reinterpret_cast<float4*>(dst)[i] = keep_fp32 ? make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3])
+                                                  : make_float4(round_tf32(f[4 * i]), round_tf32(f[4 * i + 1]),
+                                                                round_tf32(f[4 * i + 2]), round_tf32(f[4 * i + 3]));
 }
+__device__ __forceinline__ void zc_store16(__nv_bfloat16* dst, const float (&f)[16], int) { zc_store16(dst, f); }
 
 // ---- compile-time tap tables ---------------------------------------------------------------------
 // The MMA issuer must not do per-tap address arithmetic in the vector datapath: tcgen05.mma takes its
@@ -216,6 +222,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer: weights (once, or a ring) and halo slabs (a ring running ahead across tiles) =====
     {
+      if (p.wait_first) pdl_wait();                 // the weights were repacked by a kernel earlier in this stream
       if (p.resident) {
         if (elect_one_sync()) {
           mbar_expect_tx(full_b(0), static_cast<uint32_t>(n_taps) * kBBytes);
@@ -431,7 +438,8 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int t = 0;
     int store_step = 0;                           // TMA-store epilogue: 32-column steps since the kernel started
     OutT* const out_base = reinterpret_cast<OutT*>(p.out);
-    const float slope = p.act == ACT_LEAKY ? 0.2f : 0.0f;
+    // max(v, slope * v): LeakyReLU (0.2), ReLU (0) or the identity (1: the training forward stores the raw sums)
+    const float slope = p.act == ACT_LEAKY ? 0.2f : (p.act == ACT_RELU ? 0.0f : 1.0f);
     const int cp_log2 = 31 - __clz(p.cout_phase), cp_mask = p.cout_phase - 1;   // channels per phase: a power of two
     const uint32_t out_pitch = p.out_pitch, out_coff = p.out_coff;
     if constexpr (kStoreUnits > 0) {
@@ -580,7 +588,7 @@ zc_conv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             f[i + 2] = fmaxf(t2, fmaf(slope, t2, 0.0f));
             f[i + 3] = fmaxf(t3, fmaf(slope, t3, 0.0f));
           }
-          zc_store16(dst, f);
+          zc_store16(dst, f, p.keep_fp32);
         }
       }
       }
@@ -733,9 +741,11 @@ int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
   a.transposed = g.transposed ? 1 : 0; a.n_total = n_total;
   const size_t total = static_cast<size_t>(n_total) * sch.n_taps * row;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256 > 2368 ? 2368 : (total + 255) / 256);
-  if (tf32) zc_pack_weights_kernel<float><<<blocks, 256, 0, st>>>(plan->w_fold[li], a, static_cast<float*>(z.d_weights));
-  else zc_pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(plan->w_fold[li], a, static_cast<__nv_bfloat16*>(z.d_weights));
-  SVS_CHECK_LAUNCH("zc_pack_weights_kernel");
+  if (plan->w_fold[li]) {                              // a training plan has no weights yet: zc_repack_layer() per step
+    if (tf32) zc_pack_weights_kernel<float><<<blocks, 256, 0, st>>>(plan->w_fold[li], a, static_cast<float*>(z.d_weights));
+    else zc_pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(plan->w_fold[li], a, static_cast<__nv_bfloat16*>(z.d_weights));
+    SVS_CHECK_LAUNCH("zc_pack_weights_kernel");
+  }
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(sch.n_taps) * row, static_cast<cuuint64_t>(n_total)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(sch.n_taps) * row_bytes};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(row), static_cast<cuuint32_t>(n_total)};
@@ -748,6 +758,23 @@ int zc_plan_layer(svs_unet_plan* plan, int li, cudaStream_t st) {
   rc = encode_tensor_map(&z.tmap_b_quarter, tf32, 2, z.d_weights, dims, strides, box_q, row_bytes);
   if (rc != SVS_OK) return rc;
   z.enabled = true;
+  return SVS_OK;
+}
+
+// (Re)packs layer li's weights from w_fold [25][cin][cout] (stream ordered; the training step calls it every iteration)
+int zc_repack_layer(svs_unet_plan* plan, int li, const float* w_fold, cudaStream_t st) {
+  const LayerGeom& g = kLayers[li];
+  ZcLayer& z = plan->zc[li];
+  if (!z.enabled) return fail(SVS_ERR_INVALID_ARG, "zc_repack_layer: layer has no zero-copy plan");
+  const bool tf32 = plan->precision == SVS_PRECISION_TF32;
+  ZcPackArgs a{};
+  a.sch = z.sch; a.row_elems = z.row_elems; a.ct = kBufGeom[g.in_buf].c; a.in_coff = g.in_coff; a.cin = g.cin;
+  a.cout = g.cout; a.transposed = g.transposed ? 1 : 0; a.n_total = z.n_total;
+  const size_t total = static_cast<size_t>(z.n_total) * z.sch.n_taps * z.row_elems;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256 > 2368 ? 2368 : (total + 255) / 256);
+  if (tf32) zc_pack_weights_kernel<float><<<blocks, 256, 0, st>>>(w_fold, a, static_cast<float*>(z.d_weights));
+  else zc_pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w_fold, a, static_cast<__nv_bfloat16*>(z.d_weights));
+  SVS_CHECK_LAUNCH("zc_pack_weights_kernel");
   return SVS_OK;
 }
 
@@ -797,6 +824,17 @@ static int zc_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const ZcPar
 }
 
 int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int batch, cudaStream_t st) {
+  const LayerGeom& g = kLayers[li];
+  ZcIo io;
+  io.in = ws.buf[g.in_buf]; io.out = ws.buf[g.out_buf];
+  io.out_pitch = kBufGeom[g.out_buf].c; io.out_coff = g.out_coff;
+  io.bias = plan->b_fold[li]; io.act = g.act;
+  return zc_launch_layer_io(plan, li, io, batch, st);
+}
+
+// The same launch on explicit buffers: the training forward reads the fp32 concat buffer of the layer's input and
+// writes the raw sums (bias, no activation, no TF32 rounding) into the dense pre-BatchNorm buffer z.
+int zc_launch_layer_io(const svs_unet_plan* plan, int li, const ZcIo& io, int batch, cudaStream_t st) {
   const ZcLayer& z = plan->zc[li];
   const LayerGeom& g = kLayers[li];
   const bool tf32 = plan->precision == SVS_PRECISION_TF32;
@@ -814,7 +852,7 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
     }
     const cuuint32_t box[5] = {static_cast<cuuint32_t>(z.row_elems), kZcPw, 1, kZcPh, 1};
     // narrow rows: do not let the L2 promote the request to the whole 128- / 256-byte pixel neighbourhood
-    int rc = encode_tensor_map(&ta, tf32, 5, ws.buf[g.in_buf], dims, strides, box, z.row_bytes,
+    int rc = encode_tensor_map(&ta, tf32, 5, const_cast<void*>(io.in), dims, strides, box, z.row_bytes,
                                z.row_bytes < 128 ? (z.row_bytes >= 64 ? 64 : 0) : 256);
     if (rc != SVS_OK) return rc;
   }
@@ -825,14 +863,16 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   p.ntw = gw / kZcBw; p.nth = gh / kZcBh;
   p.m_tiles = p.ntw * p.nth * batch;
   p.batch = batch;
-  p.out = ws.buf[g.out_buf];
-  p.out_pitch = kBufGeom[g.out_buf].c; p.out_coff = g.out_coff;
+  p.out = io.out;
+  p.out_pitch = io.out_pitch; p.out_coff = io.out_coff;
   p.hout = g.hout; p.wout = g.wout;
   p.out_scale = g.transposed ? 2 : 1;
-  p.bias = plan->b_fold[li];
+  p.bias = io.bias;
   p.cout_phase = g.cout;
   p.merged = g.transposed ? 1 : 0;
-  p.act = g.act;
+  p.act = io.act;
+  p.keep_fp32 = io.keep_fp32;
+  p.wait_first = io.wait_first;
   p.resident = z.resident ? 1 : 0;
   p.dbg = (g_tc_dbg_layer == li) ? g_tc_dbg : nullptr;
   const int n = z.n_total;
@@ -849,13 +889,13 @@ int zc_launch_layer(const svs_unet_plan* plan, int li, const Workspace& ws, int 
   if (tma_store && !tf32 && !experiments && (li == 2 || li == 3 || li == 8 || li == 10)) {
     // 5-D output view (channel, px, x, py, batch * grid rows + y); conv layers: px = py = 1
     CUtensorMap to;
-    const cuuint64_t pitch = kBufGeom[g.out_buf].c, sc = g.transposed ? 2 : 1;
+    const cuuint64_t pitch = io.out_pitch, sc = g.transposed ? 2 : 1;
     const cuuint64_t dims[5] = {pitch, sc, static_cast<cuuint64_t>(gw), sc, static_cast<cuuint64_t>(gh) * batch};
     const cuuint64_t strides[4] = {pitch * es, sc * pitch * es, static_cast<cuuint64_t>(g.wout) * pitch * es,
                                    sc * g.wout * pitch * es};
     const int box_cols = g.cout < 32 ? g.cout : 32;
     const cuuint32_t box[5] = {static_cast<cuuint32_t>(box_cols), 1, kZcBw, 1, kZcBh};
-    int rc = encode_tensor_map(&to, tf32, 5, ws.buf[g.out_buf], dims, strides, box, box_cols * es, 0);
+    int rc = encode_tensor_map(&to, tf32, 5, io.out, dims, strides, box, box_cols * es, 0);
     if (rc != SVS_OK) return rc;
 #define SVS_ZC_STORE(LI, N, AS, BS, RES, TAPS, ROW, UNITS)                                              \
     if (li == LI && n == N && z.resident == RES && z.row_bytes == ROW && z.sch.n_slabs == TAPS::kSlabs && \
