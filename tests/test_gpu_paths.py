@@ -89,3 +89,14 @@ print("ok")
     env = dict(os.environ, SVS_ROOT=ROOT, **dict([flag.split("=")]))
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("flag", ["SVS_TRAIN_ZC=0", "SVS_TRAIN_FORK=0", "SVS_WGRAD_GROUPED=0"])
+def test_training_variants_match_reference_goldens(flag):
+    # the training step's opt-out switches (im2col kernels for the forward of conv2-4 / deconv3-5, weight gradients on
+    # the caller's stream, one-instruction-per-tap wgrad) run the reference-golden tests of test_gpu_train.py unchanged
+    env = dict(os.environ, **dict([flag.split("=")]))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_train.py"), "-x", "-q",
+                        "-k", "golden or bit_reproducible or batch_64 or equals_the_eager"], capture_output=True, text=True, env=env,
+                       timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
