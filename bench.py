@@ -23,6 +23,7 @@ CUDA-event timed on the launching stream, max over ranks.
                    the measured HBM copy bandwidth, on the 150-song corpus.
 * ``tf32``         the precision-matched path (reference arithmetic is fp32 / TF32 under cuDNN): graph-timed value,
                    e2e and roofline against a TF32 matmul peak measured here the way MEASURED_PEAKS does bf16.
+* ``two_in_flight``   informational: the same forward with TWO 64-patch batches in flight on two streams
 * ``cudnn_baseline``  informational: the same nn.Module layer list through torch eager + cuDNN on this B200
                    (fp32/TF32 NCHW as reference inference.py:40 would run it, and bf16 channels_last as its best
                    case) — never on the product path.
